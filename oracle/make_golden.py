@@ -1,0 +1,147 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF in the build container.
+
+    python -m oracle.make_golden            (needs /root/reference; CPU only)
+
+The reference has no tests and no golden vectors, so the known answers are the
+outputs of its own functions on small seeded inputs:
+
+* vlad_matmuls_per_cluster, nbrMasksAGGFastSingle, get_matches, weighted_borda_count, calc_recall,
+  normalizeFeat: called unmodified (oracle/ref_shim.py import).
+* seg_vlad_gpu_single_img / vlad_single hard-code .to('cuda') (func_vpr.py:1082-1096, 1145) and call
+  vlad_matmuls_per_cluster with its default device='cuda' (:1181): their
+  source text is taken with inspect.getsource, the literal 'cuda' is replaced by 'cpu', and the
+  patched functions are executed -- same lines, same arithmetic, CPU device.
+
+The fixtures are small (< 1 MB total) and are what the CUDA path and the oracle are both held to on
+the GPU box, where /root/reference does not exist.
+"""
+from __future__ import annotations
+
+import inspect
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from revisit_anything_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _cpu_patched(ref):
+    ns = dict(vars(ref))
+    for name in ("vlad_matmuls_per_cluster", "vlad_single", "seg_vlad_gpu_single_img"):
+        src = inspect.getsource(getattr(ref, name))
+        src = src.replace("'cuda'", "'cpu'").replace('"cuda"', '"cpu"')
+        exec(compile(src, f"<reference {name} patched cuda->cpu>", "exec"), ns)
+    return ns["seg_vlad_gpu_single_img"], ns["vlad_single"]
+
+
+def agg_case(ref, seg_vlad_img, name, D, H, W, S, order, seed, centers=None, col_stride=1,
+             normalized=True):
+    cfg = {"desired_height": H, "desired_width": W}
+    dh, dw = H // 14, W // 14
+    if centers is None:
+        centers = synth.make_centers(32, D, seed)
+    tokens = synth.make_tokens(D, dh, dw, seed, centers, normalized=normalized)
+    masks = synth.make_masks(S, H // 2, W // 2, seed)
+    adj = ref.nbrMasksAGGFastSingle(masks, order) if order else None
+    ind = np.empty((H, W, 2), dtype="int32")
+    for i in range(H):
+        for j in range(W):
+            ind[i, j] = (np.clip(i // 14, 0, dh - 1), np.clip(j // 14, 0, dw - 1))
+    ind_flat = torch.tensor(np.ravel_multi_index(ind.reshape(-1, 2).T, (dh, dw)))
+    gd = seg_vlad_img(ind_flat, ind, tokens.clone(), "img", masks, centers, cfg, desc_dim=D, adj_mat=adj)
+    gd = gd.numpy()
+    cols = np.arange(0, gd.shape[1], col_stride)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        tokens=tokens.numpy(), masks=np.asarray(masks), centers=centers.numpy(),
+        adj=(adj.numpy() if adj is not None else np.zeros((0, 0), bool)),
+        order=order, H=H, W=W, cols=cols, vlad_cols=gd[:, cols],
+        row_block_norms=np.linalg.norm(gd.reshape(gd.shape[0], 32, D), axis=2))
+    print(name, gd.shape, "->", cols.size, "cols kept")
+
+
+def vote_case(ref, name, n_qimg, segs, n_rimg, rsegs, seed, kv=50, n=5, dup_sims=False):
+    rng = np.random.RandomState(seed)
+    Nq, Nr = n_qimg * segs, n_rimg * rsegs
+    im_inds_ref = (np.arange(Nr) // rsegs).astype(np.int64)
+    matches = np.empty((Nq, kv), dtype=np.int64)
+    for q in range(Nq):
+        true_img = (q // segs) % n_rimg
+        pool_true = np.where(im_inds_ref == true_img)[0]
+        m = rng.choice(Nr, size=kv, replace=False)
+        hit = rng.rand(kv) < 0.08
+        m[hit] = rng.choice(pool_true, size=int(hit.sum()))
+        matches[q] = m
+    d2 = np.sort(rng.uniform(0.2, 1.9, size=(Nq, kv)).astype(np.float32), axis=1)
+    if dup_sims:  # many exactly equal sims -> exercises tie order (insertion order) of the vote
+        d2 = (np.round(d2 * 8) / 8).astype(np.float32)
+    sims = (2 - d2).astype(np.float32)
+    seg_range = [np.arange(i * segs, (i + 1) * segs) for i in range(n_qimg)]
+    gt = [list(np.arange(i - 1, i + 2)) if i % 3 else list(np.arange(i + 3, i + 6)) for i in range(n_qimg)]
+    preds = ref.get_matches(matches, gt, sims, seg_range, im_inds_ref, n=n,
+                            method="max_seg_topk_wt_borda_Im")
+    full = []
+    lo, hi = np.min(sims), np.max(sims)
+    for i in range(n_qimg):
+        m_t = matches[seg_range[i]].T.tolist()
+        s_t = ((sims[seg_range[i]].T - lo) / (hi - lo)).tolist()
+        pairs = [list(zip(im_inds_ref[m_t[k]], s_t[k])) for k in range(len(s_t))]
+        full.append(np.asarray(ref.weighted_borda_count(*pairs), dtype=np.int64))
+    preds_cnt = ref.get_matches(matches, gt, sims, seg_range, im_inds_ref, n=n, method="max_seg_topk")
+    recalls = ref.calc_recall(preds, gt, n)
+    pad = lambda lst, w: np.array([list(p) + [-1] * (w - len(p)) for p in lst], dtype=np.int64)
+    wmax = max(len(f) for f in full)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"), matches=matches, sims=sims, segs=segs,
+        im_inds_ref=im_inds_ref, n_qimg=n_qimg, n=n, preds=pad(preds, n),
+        full_ranking=pad(full, wmax), preds_bincount=pad(preds_cnt, n),
+        recalls=np.asarray(recalls), gt=np.asarray(gt))
+    print(name, "recalls", recalls)
+
+
+def adjacency_case(ref, name):
+    out = {}
+    for S, order, seed in [(12, 1, 1), (12, 2, 1), (12, 3, 1), (40, 3, 2), (3, 3, 3), (2, 1, 4), (1, 2, 5)]:
+        masks = synth.make_masks(S, 60, 80, seed)
+        adj = ref.nbrMasksAGGFastSingle(masks, order)
+        out[f"masks_S{S}_o{order}"] = np.asarray(masks)
+        out[f"adj_S{S}_o{order}"] = adj.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "ok")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_shim.load()
+    seg_vlad_img, _ = _cpu_patched(ref)
+    torch.manual_seed(17)
+    np.random.seed(17)
+    # small-D cases (full output kept)
+    agg_case(ref, seg_vlad_img, "agg_small_o2", D=48, H=84, W=112, S=7, order=2, seed=11)
+    agg_case(ref, seg_vlad_img, "agg_small_o0", D=48, H=84, W=112, S=5, order=0, seed=12)
+    agg_case(ref, seg_vlad_img, "agg_small_S3", D=32, H=70, W=98, S=3, order=3, seed=13)
+    agg_case(ref, seg_vlad_img, "agg_unnorm_o1", D=64, H=98, W=126, S=9, order=1, seed=14,
+             normalized=False)
+    # real vocabulary (17places 'indoor' domain, place_rec_global_config.py:35), D_t = 1536
+    voc = os.path.join(ref_shim.REF_ROOT, "cache/vocabulary/dinov2_vitg14/l31_value_c32/indoor/c_centers.pt")
+    centers = torch.load(voc, map_location="cpu").float().contiguous()
+    agg_case(ref, seg_vlad_img, "agg_realvocab_o3", D=1536, H=84, W=112, S=6, order=3, seed=15,
+             centers=centers, col_stride=61)
+    vote_case(ref, "vote_a", n_qimg=6, segs=10, n_rimg=40, rsegs=10, seed=21)
+    vote_case(ref, "vote_ties", n_qimg=5, segs=7, n_rimg=12, rsegs=6, seed=22, dup_sims=True)
+    adjacency_case(ref, "adjacency")
+    # normalizeFeat
+    x = np.random.RandomState(5).randn(9, 33)
+    np.savez_compressed(os.path.join(OUT, "normalize_feat.npz"), x=x, y=ref.normalizeFeat(x.copy()))
+
+
+if __name__ == "__main__":
+    main()

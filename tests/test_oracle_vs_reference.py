@@ -1,0 +1,51 @@
+"""Oracle vs the UNMODIFIED reference functions imported live (build container only; skipped on the
+GPU box where /root/reference does not exist).  Randomised inputs beyond the committed goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_shim
+from oracle import segvlad_oracle as O
+from revisit_anything_b200 import synth
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return ref_shim.load()
+
+
+@pytest.mark.parametrize("seed,S,order", [(1, 11, 3), (2, 5, 1), (3, 2, 2), (4, 9, 0)])
+def test_aggregation_vs_reference(ref, seed, S, order):
+    D, dh, dw = 40, 5, 7
+    centers = synth.make_centers(32, D, seed)
+    x = O.normalize_tokens(synth.make_tokens(D, dh, dw, seed, centers).reshape(D, -1))
+    masks = synth.make_masks(S, 35, 49, seed)
+    member = torch.from_numpy(O.mask_to_patch_membership(masks, 70, 98))
+    adj = ref.nbrMasksAGGFastSingle(masks, order) if order else None
+    want, lab_ref = ref_shim.vlad_single_cpu(ref, x, centers, member, adj)
+    got, lab, _ = O.vlad_single(x, centers, member, adj)
+    assert torch.equal(lab, lab_ref)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=1e-13)
+    if order:
+        np.testing.assert_array_equal(O.neighbour_adjacency(masks, order), adj.numpy())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_vote_vs_reference(ref, seed):
+    rng = np.random.RandomState(seed)
+    n_qimg, segs, Nr, kv = 7, 9, 300, 50
+    Nq = n_qimg * segs
+    im_inds_ref = np.sort(rng.randint(0, 25, size=Nr)).astype(np.int64)
+    matches = np.stack([rng.choice(Nr, kv, replace=False) for _ in range(Nq)]).astype(np.int64)
+    sims = (2 - np.sort(rng.uniform(0, 2, (Nq, kv)).astype(np.float32), axis=1)).astype(np.float32)
+    if seed == 2:
+        sims = (np.round(sims * 4) / 4).astype(np.float32)
+    seg_range = [np.arange(i * segs, (i + 1) * segs) for i in range(n_qimg)]
+    gt = [list(range(i, i + 3)) for i in range(n_qimg)]
+    want = ref.get_matches(matches, gt, sims, seg_range, im_inds_ref, n=5,
+                           method="max_seg_topk_wt_borda_Im")
+    got = O.get_matches_wt_borda(matches, n_qimg, sims, seg_range, im_inds_ref, n=5)
+    assert [list(map(int, p)) for p in got] == [list(map(int, p)) for p in want]
+    assert O.calc_recall(got, gt, 5) == ref.calc_recall(want, gt, 5)
