@@ -1,0 +1,139 @@
+/* segvlad.h -- C ABI of libsegvlad.so: the B200-native SegVLAD hot path (aggregate -> match -> vote).
+ *
+ * The reference (AnyLoc/Revisit-Anything) is pure Python and has no FFI; its "API" for this path is
+ * a handful of module-level functions.  Each entry point below names the reference
+ * function(s) it replaces (paths relative to the reference root).  The Python host layer
+ * (revisit-anything_b200/func_vpr.py, place_rec_main.py) binds these with ctypes and keeps the
+ * reference signatures.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SEGVLAD_E* code otherwise;
+ *    segvlad_last_error() gives the message of the last failure on the calling thread.
+ *  - all data pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *  - `stream` is a cudaStream_t passed as void*; every launch goes on it; no internal
+ *    synchronisation except where a function is documented to read a device flag.
+ *  - the library never allocates device memory: callers pass a workspace sized by the matching
+ *    *_workspace_bytes() query (plain device memory, 256-byte aligned, contents undefined).
+ *  - no torch types, no C++ types.
+ */
+#ifndef SEGVLAD_H_
+#define SEGVLAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGVLAD_OK 0
+#define SEGVLAD_EINVAL (-1)      /* bad shape / unsupported parameter            */
+#define SEGVLAD_ECUDA (-2)       /* CUDA runtime / driver error                  */
+#define SEGVLAD_EWORKSPACE (-3)  /* workspace too small                          */
+#define SEGVLAD_EOVERFLOW (-4)   /* candidate buffers overflowed in every schedule */
+
+#define SEGVLAD_OUT_F64 0
+#define SEGVLAD_OUT_F32 1
+
+#define SEGVLAD_TOKENS_DN 0 /* per image [D_t, N]  (reference h5 layout [1,D_t,dh,dw]) */
+#define SEGVLAD_TOKENS_ND 1 /* per image [N, D_t]                                      */
+#define SEGVLAD_TOKENS_PRENORMALIZED 2 /* OR-flag: tokens are already unit-norm, skip the L2-normalise
+                                          (vlad_single receives normalised descriptors, func_vpr.py:1096) */
+
+int segvlad_version(void);
+const char* segvlad_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Aggregation: per-(Super)Segment masked hard-assignment VLAD.
+ * Replaces  func_vpr.py:1140-1179 vlad_single  +  func_vpr.py:1181-1210 vlad_matmuls_per_cluster
+ * (called from func_vpr.py:1065-1101 seg_vlad_gpu_single / :1103-1138 seg_vlad_gpu_single_img),
+ * batched over images.
+ *
+ *  tokens        n_images * N * D_t fp32, layout per `token_layout` (NOT yet normalised: the kernel does
+ *                the channel L2-normalise of func_vpr.py:1085)
+ *  centers       [K, D_t] fp32, un-normalised (c_centers.pt)
+ *  member_bits   [S_total, ceil(N/32)] uint32: base-segment patch membership bitmask
+ *                (bit p%32 of word p/32 = mask_idx[s,p] of func_vpr.py:1090-1092)
+ *  seg_offsets_host [n_images+1] int32 prefix sum of segments per image (HOST memory)
+ *  adj           concatenated per-image [S_i, S_i] uint8 (0/1) neighbourhood matrices
+ *                (func_vpr.py:1309-1347 output), or NULL for identity (order 0)
+ *  out           [S_total, K*D_t] fp64 (SEGVLAD_OUT_F64, the reference dtype) or fp32
+ *  labels_out    optional [n_images*N] int32 cluster label per token (NULL to skip)
+ */
+size_t segvlad_aggregate_workspace_bytes(int n_images, int N, int D_t, int K, int S_total);
+int segvlad_aggregate_batch(const float* tokens, int n_images, int N, int D_t, int token_layout,
+                            const float* centers, int K, const uint32_t* member_bits,
+                            const int32_t* seg_offsets_host, const uint8_t* adj, void* out,
+                            int out_dtype, int32_t* labels_out, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* Inner stage alone: aggregate caller-provided residual rows [n_images*N, D_t] fp32 with caller-provided
+ * labels [n_images*N] int32.  Replaces func_vpr.py:1181-1210 vlad_matmuls_per_cluster(num_c, masks, res,
+ * clus_labels, adjMat).  Same workspace size as segvlad_aggregate_batch. */
+int segvlad_aggregate_residuals(const float* residuals, const int32_t* labels, int n_images, int N, int D_t,
+                                int K, const uint32_t* member_bits, const int32_t* seg_offsets_host,
+                                const uint8_t* adj, void* out, int out_dtype, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
+/* Pixel masks -> patch membership bitmask (func_vpr.py:1088-1092 + lookup table place_rec_main.py:187-194).
+ *  masks  [S, Hm, Wm] uint8 (0/1) at SAM resolution; nearest-neighbour upsampled to HxW, then a patch
+ *  is a member if any pixel of its (clipped) patch x patch cell is set.  member_bits [S, ceil(N/32)]. */
+int segvlad_mask_to_membership(const uint8_t* masks, int S, int Hm, int Wm, int H, int W, int patch,
+                               uint32_t* member_bits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matching: exhaustive squared-L2 kNN of query-segment descriptors against a (shard of the)
+ * reference bank.  Replaces faiss.IndexFlatL2.add/search at place_rec_main.py:53-61.
+ *
+ * A "bank" is the resident, kernel-ready form of an [n, D] fp32 descriptor matrix: two bf16 planes
+ * (hi, mid: x ~= hi + mid to 2^-17 relative) padded to a multiple of 64 columns, and fp32 squared norms.
+ */
+size_t segvlad_bank_bytes(int n, int D);
+int segvlad_bank_prepare(const float* x, int n, int D, void* bank, void* stream);
+/* fp64 input (the reference keeps segFtVLAD1/2 in fp64): optional row L2-normalise in fp64 WITHOUT eps
+ * (func_vpr.py:1673-1676 normalizeFeat, place_rec_main.py:55-56), then the fp32 cast faiss's Python
+ * wrapper performs, then the split. */
+int segvlad_bank_prepare_f64(const double* x, int n, int D, int normalize_rows, void* bank, void* stream);
+
+size_t segvlad_knn_workspace_bytes(int Nq, int Nr, int D, int k);
+/* d2_out [Nq,k] fp32 ascending (ties: smaller index first), idx_out [Nq,k] int64 = row_offset + local
+ * row; rows with fewer than k refs are padded with (+inf, -1) like faiss.
+ * Synchronises `stream` once at the end to read the overflow flag (and re-runs with the conservative
+ * chunk schedule if any candidate buffer overflowed). */
+int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D,
+                int k, float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
+                void* stream);
+/* Same contract on the raw fp32 matrices with plain fp32 FFMA inner products (no tensor cores):
+ * the on-device cross-check for the tcgen05 path (tests / debugging); same workspace size. */
+int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, int64_t row_offset, int D, int k,
+                     float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* k-way merge of per-shard results after the all-gather: parts are [G, Nq, k]. */
+int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, int Nq, int k,
+                       float* d2_out, int64_t* idx_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Vote: segment hits -> ranked reference images.
+ * Replaces func_vpr.py:80-243 get_matches, branch :207-224 ("max_seg_topk_wt_borda_Im") with
+ * func_vpr.py:61-77 weighted_borda_count, and the integer bincount of :118-125 ("max_seg_topk").
+ *
+ *  matches [Nq, ld] int64 (first k_vote columns used), sims [Nq, ld] fp32 (or d2 if sims_is_d2 != 0:
+ *  sims = 2 - d2 in fp32, place_rec_main.py:78-81)
+ *  qimg_offsets [n_qimg+1] int32: query image i owns rows [off[i], off[i+1])  (segRangeQuery)
+ *  rseg_to_rimg [Nr] int32 (imIndsRef)
+ *  preds        [n_qimg, n_pred] int32 ref-image ids, -1 padded;  pred_scores [n_qimg, n_pred] fp64
+ *  scores_dense / counts_dense: optional [n_qimg, n_rimg] fp64 / int32 (NULL to skip)
+ *  minmax_out   optional [2] fp32 (global min, max of sims)
+ */
+size_t segvlad_vote_workspace_bytes(int Nq, int k_vote, int n_qimg, int max_segs_per_qimg);
+int segvlad_vote(const int64_t* matches, const float* sims, int ld, int sims_is_d2, int k_vote, int Nq,
+                 const int32_t* qimg_offsets, int n_qimg, int max_segs_per_qimg,
+                 const int32_t* rseg_to_rimg, int Nr, int n_rimg, int n_pred, int32_t* preds,
+                 double* pred_scores, double* scores_dense, int32_t* counts_dense, float* minmax_out,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGVLAD_H_ */

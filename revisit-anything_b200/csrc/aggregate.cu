@@ -1,0 +1,611 @@
+// Per-(Super)Segment masked hard-assignment VLAD aggregation for sm_100a.
+//
+// Replaces (batched over images) the reference chain
+//   seg_vlad_gpu_single  func_vpr.py:1065-1101  -> vlad_single :1140-1179 -> vlad_matmuls_per_cluster :1181-1210
+//
+// Pipeline (all on the caller's stream, no host sync, no float atomics => bit-reproducible):
+//   normalize_centers   c_hat = c / max(||c||,eps)                       (func_vpr.py:1145)
+//   assign_*            per token: ||x||, argmax_k <x, c_hat_k>, residual row r = x/max(||x||,eps) - c[label]
+//                                                                      (func_vpr.py:1085, 1146, 1151)
+//   cluster_lists       counting sort of the image's tokens by label (replaces torch.where per cluster :1197)
+//   superseg_union      member'[s] = OR_t adj[s,t] member[t]            (func_vpr.py:1200, bitmask form)
+//   group_transpose     token-major membership words for groups of SEG_GROUP segments
+//   nonempty            predicted number of non-empty clusters per segment (row norm)
+//   aggregate           V[s,k,:] = sum_{p in seg s, label k} (double) r_p ; intra-norm ; row-norm ; store
+//                                                                      (func_vpr.py:1201-1205)
+//   rownorm_fixup       exact handling of blocks with 0 < ||V|| < eps or exact cancellation
+//
+// HBM-bound by design: tokens are read once (+ once from L2), the [S, K*D] output is written once with
+// streaming stores.  Accumulation is fp64 like the reference (the addends are fp32 values, so the sums
+// are exact to ~1e-16 and independent of the summation order in practice).
+#include "common.cuh"
+
+namespace segvlad {
+
+constexpr int kSegGroup = 8;       // segments per aggregate CTA (register tile)
+constexpr int kTokTile = 32;       // tokens per assign CTA
+constexpr int kAssignWarps = 8;
+constexpr float kEpsF = 1e-12f;
+constexpr double kEpsD = 1e-12;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void normalize_centers_kernel(const float* __restrict__ c, int K, int D,
+                                         float* __restrict__ chatT, int Kp) {
+  // one block per centre; chatT is [D][Kp] (k fastest) so a warp can fetch 32 consecutive k with LDG.128
+  int k = blockIdx.x;
+  __shared__ float s_w[32];
+  float ss = 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v = c[(size_t)k * D + d];
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? s_w[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) s_w[0] = fmaxf(sqrtf(v), kEpsF);
+  }
+  __syncthreads();
+  float nrm = s_w[0];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) chatT[(size_t)d * Kp + k] = c[(size_t)k * D + d] / nrm;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Assignment + residual rows, tokens in the reference's [D, N] layout (lane = token => coalesced).
+__global__ void __launch_bounds__(kAssignWarps * 32)
+assign_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __restrict__ centers,
+                 const float* __restrict__ chatT, int K, int Kp, int prenorm, float* __restrict__ R,
+                 int* __restrict__ labels) {
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kTokTile;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int p = p0 + lane;
+  const bool valid = p < N;
+  const float* tok = tokens + (size_t)b * D * N;
+  const int dchunk = (D + kAssignWarps - 1) / kAssignWarps;
+  const int d0 = min(D, w * dchunk), d1 = min(D, d0 + dchunk);
+
+  __shared__ float s_part[kAssignWarps][32][33];
+  __shared__ float s_ss[kAssignWarps][32];
+  __shared__ float s_nrm[32];
+  __shared__ int s_lab[32];
+
+  float ss = 0.f, bestv = -INFINITY;
+  int besti = 0;
+  for (int kc = 0; kc < K; kc += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int d = d0; d < d1; ++d) {
+      float x = valid ? __ldg(tok + (size_t)d * N + p) : 0.f;
+      if (kc == 0) ss = fmaf(x, x, ss);
+      const float4* cr = reinterpret_cast<const float4*>(chatT + (size_t)d * Kp + kc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 cv = __ldg(cr + j);
+        acc[4 * j + 0] = fmaf(x, cv.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(x, cv.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(x, cv.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(x, cv.w, acc[4 * j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s_part[w][j][lane] = acc[j];
+    if (kc == 0) s_ss[w][lane] = ss;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32 / kAssignWarps; ++kk) {
+      int k = w * (32 / kAssignWarps) + kk;
+      float t = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < kAssignWarps; ++ww) t += s_part[ww][k][lane];
+      s_part[0][k][lane] = t;  // distinct k per warp: no hazard with the reads above
+    }
+    __syncthreads();
+    if (w == 0) {
+      for (int k = 0; k < 32 && kc + k < K; ++k) {
+        float v = s_part[0][k][lane];
+        if (v > bestv) { bestv = v; besti = kc + k; }  // strict '>' => first index on ties (torch.argmax)
+      }
+    }
+    __syncthreads();
+  }
+  if (w == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kAssignWarps; ++ww) t += s_ss[ww][lane];
+    s_nrm[lane] = prenorm ? 1.0f : fmaxf(sqrtf(t), kEpsF);
+    s_lab[lane] = besti;
+    if (valid) labels[(size_t)b * N + p] = besti;
+  }
+  __syncthreads();
+  // residual rows, transposed to token-major through a padded smem tile (per warp, its own d slice)
+  const float nrm = s_nrm[lane];
+  for (int dd = d0; dd < d1; dd += 32) {
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      int d = dd + r;
+      float x = (d < d1 && valid) ? __ldg(tok + (size_t)d * N + p) : 0.f;
+      s_part[w][r][lane] = x / nrm;
+    }
+    __syncwarp();
+    const int d = dd + lane;
+    if (d < d1) {
+      for (int t = 0; t < 32; ++t) {
+        int pp = p0 + t;
+        if (pp < N)
+          R[((size_t)b * N + pp) * D + d] = s_part[w][lane][t] - __ldg(centers + (size_t)s_lab[t] * D + d);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// Token-major [N, D] input: one warp per token, lanes stride the channels, warp-shuffle reductions.
+__global__ void __launch_bounds__(256)
+assign_nd_kernel(const float* __restrict__ tokens, int N, int D, const float* __restrict__ centers,
+                 const float* __restrict__ chatT, int K, int Kp, int prenorm, float* __restrict__ R,
+                 int* __restrict__ labels) {
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= N) return;
+  const float* x = tokens + ((size_t)b * N + p) * D;
+  float ss = 0.f, bestv = -INFINITY;
+  int besti = 0;
+  for (int kc = 0; kc < K; kc += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      float v = __ldg(x + d);
+      if (kc == 0) ss = fmaf(v, v, ss);
+      const float4* cr = reinterpret_cast<const float4*>(chatT + (size_t)d * Kp + kc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 cv = __ldg(cr + j);
+        acc[4 * j + 0] = fmaf(v, cv.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(v, cv.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(v, cv.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(v, cv.w, acc[4 * j + 3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = warp_sum(acc[j]);
+      if (kc + j < K && v > bestv) { bestv = v; besti = kc + j; }
+    }
+  }
+  ss = warp_sum(ss);
+  const float nrm = prenorm ? 1.0f : fmaxf(sqrtf(ss), kEpsF);
+  if (lane == 0) labels[(size_t)b * N + p] = besti;
+  float* r = R + ((size_t)b * N + p) * D;
+  const float* c = centers + (size_t)besti * D;
+  for (int d = lane; d < D; d += 32) r[d] = __ldg(x + d) / nrm - __ldg(c + d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Counting sort of one image's tokens by label; tokens stay in ascending order inside a cluster.
+__global__ void __launch_bounds__(1024)
+cluster_lists_kernel(const int* __restrict__ labels, int N, int K, int* __restrict__ cl_ptr,
+                     int* __restrict__ cl_tok) {
+  const int b = blockIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int* lab = labels + (size_t)b * N;
+  __shared__ int s_cnt[256 + 1];
+  for (int k = w; k < K; k += nw) {
+    int c = 0;
+    for (int base = 0; base < N; base += 32) {
+      int p = base + lane;
+      c += __popc(__ballot_sync(0xffffffffu, p < N && lab[p] == k));
+    }
+    if (lane == 0) s_cnt[k] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 0; k < K; ++k) { int c = s_cnt[k]; s_cnt[k] = run; run += c; }
+    s_cnt[K] = run;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) cl_ptr[(size_t)b * (K + 1) + k] = s_cnt[k];
+  for (int k = w; k < K; k += nw) {
+    int pos = s_cnt[k];
+    for (int base = 0; base < N; base += 32) {
+      int p = base + lane;
+      bool m = p < N && lab[p] == k;
+      unsigned bal = __ballot_sync(0xffffffffu, m);
+      if (m) cl_tok[(size_t)b * N + pos + __popc(bal & ((1u << lane) - 1u))] = p;
+      pos += __popc(bal);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_image(const int* __restrict__ seg_off, int B, int s) {
+  int lo = 0, hi = B;  // largest b with seg_off[b] <= s
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (seg_off[mid] <= s) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void superseg_union_kernel(const uint32_t* __restrict__ mem, const uint8_t* __restrict__ adj,
+                                      const int* __restrict__ seg_off, const long long* __restrict__ adj_off,
+                                      int B, int W, uint32_t* __restrict__ sup) {
+  const int s = blockIdx.x;
+  const int b = find_image(seg_off, B, s);
+  const int s0 = seg_off[b], Si = seg_off[b + 1] - s0;
+  const uint8_t* arow = adj + adj_off[b] + (size_t)(s - s0) * Si;
+  for (int wd = threadIdx.x; wd < W; wd += blockDim.x) {
+    uint32_t acc = 0;
+    for (int t = 0; t < Si; ++t)
+      if (arow[t]) acc |= mem[(size_t)(s0 + t) * W + wd];
+    sup[(size_t)s * W + wd] = acc;
+  }
+}
+
+__global__ void group_transpose_kernel(const uint32_t* __restrict__ sup, const int* __restrict__ grp_seg0,
+                                       const int* __restrict__ grp_nseg, int N, int W,
+                                       uint8_t* __restrict__ memT) {
+  const int g = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int s0 = grp_seg0[g], ns = grp_nseg[g];
+  unsigned m = 0;
+  for (int j = 0; j < ns; ++j) m |= ((sup[(size_t)(s0 + j) * W + (p >> 5)] >> (p & 31)) & 1u) << j;
+  memT[(size_t)g * N + p] = (uint8_t)m;
+}
+
+// predicted #non-empty (segment, cluster) blocks per segment: one warp per segment
+__global__ void nonempty_kernel(const uint32_t* __restrict__ sup, const int* __restrict__ labels,
+                                const int* __restrict__ seg_off, int B, int N, int W,
+                                int* __restrict__ cpred) {
+  const int s = blockIdx.x, lane = threadIdx.x;
+  const int b = find_image(seg_off, B, s);
+  const int* lab = labels + (size_t)b * N;
+  uint32_t mk[4] = {0, 0, 0, 0};
+  for (int wd = lane; wd < W; wd += 32) {
+    uint32_t bits = sup[(size_t)s * W + wd];
+    while (bits) {
+      int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      int p = wd * 32 + j;
+      if (p < N) { int k = lab[p]; mk[k >> 5] |= 1u << (k & 31); }
+    }
+  }
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t v = mk[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    c += __popc(v);
+  }
+  if (lane == 0) cpred[s] = c;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename OutT> struct Store4;
+template <> struct Store4<double> {
+  static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
+    __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(c, d));
+  }
+};
+template <> struct Store4<float> {
+  static __device__ __forceinline__ void st(float* p, double a, double b, double c, double d) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4((float)a, (float)b, (float)c, (float)d));
+  }
+};
+
+// grid (n_groups_total, K); block = ceil(D/4) threads rounded to a warp; thread t owns channels 4t..4t+3
+// of kSegGroup segment accumulators (fp64).  Membership words are CTA-uniform => branch-uniform adds.
+template <typename OutT>
+__global__ void __launch_bounds__(384, 1)
+aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, const int* __restrict__ cl_tok,
+                 const uint8_t* __restrict__ memT, const int* __restrict__ grp_img,
+                 const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
+                 const int* __restrict__ cpred, int N, int D, int K, OutT* __restrict__ out,
+                 double* __restrict__ norms) {
+  const int g = blockIdx.x, k = blockIdx.y;
+  const int b = grp_img[g], s0 = grp_seg0[g], ns = grp_nseg[g];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
+  const int d = 4 * t;
+  const bool act = d < D;
+  const int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
+  const int* toks = cl_tok + (size_t)b * N;
+  const uint8_t* mrow = memT + (size_t)g * N;
+  const float* Rb = R + (size_t)b * N * D + d;
+
+  double acc[kSegGroup][4];
+#pragma unroll
+  for (int j = 0; j < kSegGroup; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+
+  constexpr int U = 4;
+  for (int i = beg; i < end; i += U) {
+    int p[U];
+    unsigned m[U];
+    float4 r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      m[u] = 0;
+      if (i + u < end) { p[u] = toks[i + u]; m[u] = mrow[p[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (m[u] && act) r[u] = __ldg(reinterpret_cast<const float4*>(Rb + (size_t)p[u] * D));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (m[u] && act) {
+#pragma unroll
+        for (int j = 0; j < kSegGroup; ++j) {
+          if ((m[u] >> j) & 1u) {
+            acc[j][0] += (double)r[u].x;
+            acc[j][1] += (double)r[u].y;
+            acc[j][2] += (double)r[u].z;
+            acc[j][3] += (double)r[u].w;
+          }
+        }
+      }
+    }
+  }
+
+  __shared__ double s_red[12][kSegGroup];
+  __shared__ double s_scale[kSegGroup];
+#pragma unroll
+  for (int j = 0; j < kSegGroup; ++j) {
+    double ss = acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1] + acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3];
+    ss = warp_sum(ss);
+    if (lane == 0) s_red[w][j] = ss;
+  }
+  __syncthreads();
+  if (t < kSegGroup) {
+    double tot = 0.0;
+    for (int ww = 0; ww < nw; ++ww) tot += s_red[ww][t];
+    double nrm = sqrt(tot);
+    double sc = 0.0;
+    if (t < ns) {
+      norms[(size_t)(s0 + t) * K + k] = nrm;
+      double rown = fmax(sqrt((double)cpred[s0 + t]), kEpsD);
+      sc = (1.0 / fmax(nrm, kEpsD)) * (1.0 / rown);
+    }
+    s_scale[t] = sc;
+  }
+  __syncthreads();
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < kSegGroup; ++j) {
+      if (j < ns) {
+        double sc = s_scale[j];
+        OutT* o = out + (size_t)(s0 + j) * K * D + (size_t)k * D + d;
+        Store4<OutT>::st(o, acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
+      }
+    }
+  }
+}
+
+// Row norm as the reference computes it: sqrt(sum_k (||V_k|| / max(||V_k||,eps))^2).  The aggregate
+// kernel used sqrt(#non-empty blocks); they differ only if some non-empty block has ||V_k|| < eps
+// (exact cancellation / zero residuals).  Those rows are rescaled here (normally: none).
+template <typename OutT>
+__global__ void rownorm_fixup_kernel(const double* __restrict__ norms, const int* __restrict__ cpred, int K,
+                                     size_t row_len, OutT* __restrict__ out) {
+  const int s = blockIdx.x;
+  __shared__ double s_factor;
+  if (threadIdx.x == 0) {
+    double tsum = 0.0;
+    for (int k = 0; k < K; ++k) {
+      double n = norms[(size_t)s * K + k];
+      double q = n / fmax(n, kEpsD);
+      tsum += q * q;
+    }
+    double m_true = sqrt(tsum), m_pred = sqrt((double)cpred[s]);
+    s_factor = (m_true == m_pred) ? 1.0 : fmax(m_pred, kEpsD) / fmax(m_true, kEpsD);
+  }
+  __syncthreads();
+  const double f = s_factor;
+  if (f == 1.0) return;
+  OutT* o = out + (size_t)s * row_len;
+  for (size_t i = threadIdx.x; i < row_len; i += blockDim.x) o[i] = (OutT)((double)o[i] * f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pixel masks -> patch membership bits (func_vpr.py:1088-1092).  One thread per (segment, patch).
+__global__ void mask_to_membership_kernel(const uint8_t* __restrict__ masks, int S, int Hm, int Wm, int H,
+                                          int W, int patch, int dh, int dw, uint32_t* __restrict__ bits,
+                                          int Wd) {
+  const int s = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = dh * dw;
+  bool any = false;
+  if (p < N) {
+    const int pi = p / dw, pj = p % dw;
+    const int i0 = pi * patch, i1 = (pi == dh - 1) ? H : i0 + patch;
+    const int j0 = pj * patch, j1 = (pj == dw - 1) ? W : j0 + patch;
+    const float sh = (float)Hm / (float)H, sw = (float)Wm / (float)W;  // torch 'nearest' source index
+    const uint8_t* m = masks + (size_t)s * Hm * Wm;
+    for (int i = i0; i < i1 && !any; ++i) {
+      int si = min((int)floorf((float)i * sh), Hm - 1);
+      for (int j = j0; j < j1; ++j) {
+        int sj = min((int)floorf((float)j * sw), Wm - 1);
+        if (m[(size_t)si * Wm + sj]) { any = true; break; }
+      }
+    }
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, any);
+  if ((threadIdx.x & 31) == 0 && (p >> 5) < Wd) bits[(size_t)s * Wd + (p >> 5)] = bal;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct AggLayout {
+  float* chatT; float* R; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint8_t* memT;
+  int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
+  size_t total;
+};
+
+static AggLayout carve_agg(void* ws, int B, int N, int D, int K, int S_total) {
+  Carver c(ws);
+  AggLayout L;
+  const int Kp = (int)align_up(K, 32), W = (N + 31) / 32;
+  const int max_groups = S_total / kSegGroup + B;  // sum_b ceil(S_b / G) <= S_total/G + B
+  L.chatT = c.take<float>((size_t)D * Kp);
+  L.R = c.take<float>((size_t)B * N * D);
+  L.labels = c.take<int>((size_t)B * N);
+  L.cl_ptr = c.take<int>((size_t)B * (K + 1));
+  L.cl_tok = c.take<int>((size_t)B * N);
+  L.sup = c.take<uint32_t>((size_t)S_total * W);
+  L.memT = c.take<uint8_t>((size_t)max_groups * N);
+  L.cpred = c.take<int>(S_total);
+  L.norms = c.take<double>((size_t)S_total * K);
+  L.seg_off = c.take<int>(B + 1);
+  L.adj_off = c.take<long long>(B + 1);
+  L.grp_img = c.take<int>(max_groups);
+  L.grp_seg0 = c.take<int>(max_groups);
+  L.grp_nseg = c.take<int>(max_groups);
+  L.total = c.total();
+  return L;
+}
+
+}  // namespace segvlad
+
+using namespace segvlad;
+
+extern "C" size_t segvlad_aggregate_workspace_bytes(int n_images, int N, int D_t, int K, int S_total) {
+  if (n_images <= 0 || N <= 0 || D_t <= 0 || K <= 0 || S_total < 0) return 0;
+  return carve_agg(nullptr, n_images, N, D_t, K, S_total).total;
+}
+
+// Common driver.  residuals_in != nullptr: skip normalise/assign and aggregate the caller's residual
+// rows [B*N, D] fp32 with the caller's labels (vlad_matmuls_per_cluster drop-in, func_vpr.py:1181).
+static int aggregate_driver(const float* tokens, const float* residuals_in, const int32_t* labels_in, int B, int N,
+                            int D, int token_layout, const float* centers, int K, const uint32_t* member_bits,
+                            const int32_t* seg_offsets_host, const uint8_t* adj, void* out, int out_dtype,
+                            int32_t* labels_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  SV_REQUIRE(B > 0 && N > 0 && D > 0 && K > 0, "aggregate: non-positive shape");
+  SV_REQUIRE(D % 4 == 0 && D <= 1536, "aggregate: D_t must be a multiple of 4 and <= 1536 (got %d)", D);
+  SV_REQUIRE(K <= 128, "aggregate: K must be <= 128 (got %d)", K);
+  const int layout = token_layout & 1, prenorm = (token_layout & SEGVLAD_TOKENS_PRENORMALIZED) ? 1 : 0;
+  SV_REQUIRE((token_layout & ~3) == 0, "aggregate: bad token_layout");
+  SV_REQUIRE(out_dtype == SEGVLAD_OUT_F64 || out_dtype == SEGVLAD_OUT_F32, "aggregate: bad out_dtype");
+  SV_REQUIRE(seg_offsets_host && seg_offsets_host[0] == 0, "aggregate: seg_offsets_host[0] must be 0");
+  const int S_total = seg_offsets_host[B];
+  for (int b = 0; b < B; ++b)
+    SV_REQUIRE(seg_offsets_host[b + 1] >= seg_offsets_host[b], "aggregate: seg_offsets not monotone");
+  if (S_total == 0) return SEGVLAD_OK;
+  AggLayout L = carve_agg(workspace, B, N, D, K, S_total);
+  if (workspace_bytes < L.total || !workspace) {
+    set_error("aggregate: workspace %zu < required %zu", workspace_bytes, L.total);
+    return SEGVLAD_EWORKSPACE;
+  }
+  const int Kp = (int)align_up(K, 32), W = (N + 31) / 32;
+
+  // host-side metadata: offsets and segment-group tables (one small H2D copy each)
+  const int max_groups = S_total / kSegGroup + B;
+  int* h = (int*)malloc(sizeof(int) * (size_t)(3 * max_groups + 2) + sizeof(long long) * (size_t)(B + 1));
+  SV_REQUIRE(h, "aggregate: host malloc failed");
+  int* h_img = h; int* h_s0 = h + max_groups; int* h_ns = h + 2 * max_groups;
+  long long* h_adj = reinterpret_cast<long long*>(h + 3 * max_groups + ((3 * max_groups) & 1));
+  int ng = 0;
+  long long ao = 0;
+  for (int b = 0; b < B; ++b) {
+    int s0 = seg_offsets_host[b], Si = seg_offsets_host[b + 1] - s0;
+    h_adj[b] = ao;
+    ao += (long long)Si * Si;
+    for (int g0 = 0; g0 < Si; g0 += kSegGroup) {
+      h_img[ng] = b; h_s0[ng] = s0 + g0; h_ns[ng] = min(kSegGroup, Si - g0); ++ng;
+    }
+  }
+  h_adj[B] = ao;
+  cudaError_t e = cudaMemcpyAsync(L.seg_off, seg_offsets_host, sizeof(int) * (B + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(L.adj_off, h_adj, sizeof(long long) * (B + 1), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(L.grp_img, h_img, sizeof(int) * ng, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(L.grp_seg0, h_s0, sizeof(int) * ng, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(L.grp_nseg, h_ns, sizeof(int) * ng, cudaMemcpyHostToDevice, st);
+  free(h);  // pageable-source cudaMemcpyAsync has staged the bytes before returning
+  SV_CHECK_CUDA(e);
+
+  const float* R = L.R;
+  const int* labels = L.labels;
+  if (residuals_in) {
+    R = residuals_in;
+    labels = labels_in;
+  } else {
+    // zero padding columns of chatT (k >= K) so the 32-wide loads see zeros
+    SV_CHECK_CUDA(cudaMemsetAsync(L.chatT, 0, sizeof(float) * (size_t)D * Kp, st));
+    normalize_centers_kernel<<<K, 256, 0, st>>>(centers, K, D, L.chatT, Kp);
+    SV_CHECK_LAUNCH();
+    if (layout == SEGVLAD_TOKENS_DN) {
+      dim3 grid((N + kTokTile - 1) / kTokTile, B);
+      assign_dn_kernel<<<grid, kAssignWarps * 32, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
+    } else {
+      dim3 grid((N + 7) / 8, B);
+      assign_nd_kernel<<<grid, 256, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
+    }
+    SV_CHECK_LAUNCH();
+  }
+  cluster_lists_kernel<<<B, 1024, 0, st>>>(labels, N, K, L.cl_ptr, L.cl_tok);
+  SV_CHECK_LAUNCH();
+  const uint32_t* sup = member_bits;
+  if (adj) {
+    superseg_union_kernel<<<S_total, 64, 0, st>>>(member_bits, adj, L.seg_off, L.adj_off, B, W, L.sup);
+    SV_CHECK_LAUNCH();
+    sup = L.sup;
+  }
+  group_transpose_kernel<<<dim3((N + 255) / 256, ng), 256, 0, st>>>(sup, L.grp_seg0, L.grp_nseg, N, W, L.memT);
+  SV_CHECK_LAUNCH();
+  nonempty_kernel<<<S_total, 32, 0, st>>>(sup, labels, L.seg_off, B, N, W, L.cpred);
+  SV_CHECK_LAUNCH();
+  const int threads = (int)align_up((size_t)(D / 4), 32);
+  if (out_dtype == SEGVLAD_OUT_F64) {
+    aggregate_kernel<double><<<dim3(ng, K), threads, 0, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
+                                                              L.grp_nseg, L.cpred, N, D, K, (double*)out, L.norms);
+    SV_CHECK_LAUNCH();
+    rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
+  } else {
+    aggregate_kernel<float><<<dim3(ng, K), threads, 0, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
+                                                             L.grp_nseg, L.cpred, N, D, K, (float*)out, L.norms);
+    SV_CHECK_LAUNCH();
+    rownorm_fixup_kernel<float><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (float*)out);
+  }
+  SV_CHECK_LAUNCH();
+  if (labels_out && !residuals_in)
+    SV_CHECK_CUDA(cudaMemcpyAsync(labels_out, L.labels, sizeof(int) * (size_t)B * N, cudaMemcpyDeviceToDevice, st));
+  return SEGVLAD_OK;
+}
+
+extern "C" int segvlad_aggregate_batch(const float* tokens, int B, int N, int D, int token_layout,
+                                       const float* centers, int K, const uint32_t* member_bits,
+                                       const int32_t* seg_offsets_host, const uint8_t* adj, void* out,
+                                       int out_dtype, int32_t* labels_out, void* workspace,
+                                       size_t workspace_bytes, void* stream_) {
+  SV_REQUIRE(tokens && centers && member_bits && out, "aggregate: null pointer");
+  return aggregate_driver(tokens, nullptr, nullptr, B, N, D, token_layout, centers, K, member_bits, seg_offsets_host,
+                          adj, out, out_dtype, labels_out, workspace, workspace_bytes,
+                          reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int segvlad_aggregate_residuals(const float* residuals, const int32_t* labels, int B, int N, int D, int K,
+                                           const uint32_t* member_bits, const int32_t* seg_offsets_host,
+                                           const uint8_t* adj, void* out, int out_dtype, void* workspace,
+                                           size_t workspace_bytes, void* stream_) {
+  SV_REQUIRE(residuals && labels && member_bits && out, "aggregate_residuals: null pointer");
+  return aggregate_driver(nullptr, residuals, labels, B, N, D, SEGVLAD_TOKENS_ND, nullptr, K, member_bits,
+                          seg_offsets_host, adj, out, out_dtype, nullptr, workspace, workspace_bytes,
+                          reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int segvlad_mask_to_membership(const uint8_t* masks, int S, int Hm, int Wm, int H, int W, int patch,
+                                          uint32_t* member_bits, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(S >= 0 && Hm > 0 && Wm > 0 && H >= patch && W >= patch && patch > 0, "mask_to_membership: bad shape");
+  if (S == 0) return SEGVLAD_OK;
+  const int dh = H / patch, dw = W / patch, N = dh * dw, Wd = (N + 31) / 32;
+  dim3 grid((Wd * 32 + 255) / 256, S);
+  mask_to_membership_kernel<<<grid, 256, 0, st>>>(masks, S, Hm, Wm, H, W, patch, dh, dw, member_bits, Wd);
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}

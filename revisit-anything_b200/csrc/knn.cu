@@ -1,0 +1,732 @@
+// Exhaustive squared-L2 kNN of query-segment descriptors against a reference-bank shard, sm_100a.
+//
+// Replaces faiss.IndexFlatL2.add/search at place_rec_main.py:53-61 (faiss 1.7.3 BLAS path:
+// d2 = ||q||^2 + ||r||^2 - 2<q,r>, clamped at 0, k smallest ascending).
+//
+// Structure
+//   bank_prepare        fp32 [n,D] -> bf16 hi / mid planes (x ~= hi + mid, 2^-17 rel.) + fp32 ||x||^2
+//   knn_tc_filter       persistent tcgen05 kernel: all-pairs <q,r> = hi.hi + hi.mid + mid.hi on the tensor
+//                       cores (kind::f16, bf16 in, fp32 accumulate in TMEM), TMA-fed 2-stage smem ring,
+//                       double-buffered 128x256 accumulators; the epilogue turns each inner product into d2,
+//                       compares it with the row's running threshold tau and appends survivors to the
+//                       row's candidate list (the all-pairs matrix is never written to HBM)
+//   knn_simt_filter     same epilogue behind a plain fp32 FFMA tile kernel (cross-check path)
+//   knn_refine          per row: bitonic-select the k best candidates, tighten tau; final pass sorts and
+//                       writes (d2, global index) ascending with (d2, idx) tie order
+//   merge_topk          k-way merge of per-shard lists after the all-gather
+//
+// The reference bank is scanned in rounds of geometrically growing chunks: after a chunk, tau = current
+// k-th best, so a later chunk of n refs leaves ~ n*k/seen survivors per row.  Buffers overflowing
+// (adversarially ordered banks) raise a flag; the host then re-runs with chunks <= C - k (cannot overflow).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace segvlad {
+
+constexpr int kCandCap = 4096;     // candidate slots per query row
+constexpr int kMaxK = 1024;
+constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
+constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
+constexpr int kStages = 2;
+constexpr uint32_t kStageBytes = (kTileM + kTileN) * kTileK * 2 * 2;  // hi+mid planes of Q and R tiles
+constexpr int kTcThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
+
+struct SelState {
+  float* tau;      // [rows] current k-th best d2 (+inf until k candidates seen)
+  int* cnt;        // [rows] candidates stored
+  float* cand_d2;  // [rows][kCandCap]
+  int* cand_idx;   // [rows][kCandCap]  shard-local ref row
+  int* overflow;   // [1]
+};
+
+__device__ __forceinline__ float make_d2(float qn, float rn, float ip) {
+  float v = __fsub_rn(__fadd_rn(qn, rn), 2.0f * ip);
+  return v > 0.f ? v : 0.f;  // clamp negatives (and -0, NaN) to +0 like faiss
+}
+
+// survivors of rounds >= 1: one atomic slot claim per survivor
+__device__ __forceinline__ void cand_append(const SelState& s, int row, int col, float d2) {
+  int pos = atomicAdd(s.cnt + row, 1);
+  if (pos < kCandCap) {
+    s.cand_d2[(size_t)row * kCandCap + pos] = d2;
+    s.cand_idx[(size_t)row * kCandCap + pos] = col;
+  } else {
+    *s.overflow = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bank preparation: one warp per row
+struct BankView {
+  const __nv_bfloat16* hi; const __nv_bfloat16* mid; const float* norms; int Dp;
+};
+static inline int padded_dim(int D) { return (int)align_up((size_t)D, kTileK); }
+static BankView bank_view(const void* bank, int n, int D) {
+  Carver c(const_cast<void*>(bank));
+  BankView v;
+  v.Dp = padded_dim(D);
+  v.hi = c.take<__nv_bfloat16>((size_t)n * v.Dp);
+  v.mid = c.take<__nv_bfloat16>((size_t)n * v.Dp);
+  v.norms = c.take<float>(n);
+  return v;
+}
+
+__global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, int Dp,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                                    float* __restrict__ norms) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + (size_t)row * D;
+  float ss = 0.f;
+  for (int d = lane; d < Dp; d += 32) {
+    float v = d < D ? xr[d] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[(size_t)row * Dp + d] = h;
+    mid[(size_t)row * Dp + d] = m;
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) norms[row] = ss;
+}
+
+__global__ void bank_prepare_f64_kernel(const double* __restrict__ x, int n, int D, int Dp, int normalize_rows,
+                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                                        float* __restrict__ norms) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const double* xr = x + (size_t)row * D;
+  double nrm = 1.0;
+  if (normalize_rows) {
+    double s2 = 0.0;
+    for (int d = lane; d < D; d += 32) s2 += xr[d] * xr[d];
+    nrm = sqrt(warp_sum(s2));  // no eps: a zero row becomes NaN exactly like normalizeFeat
+  }
+  float ss = 0.f;
+  for (int d = lane; d < Dp; d += 32) {
+    float v = d < D ? (float)(normalize_rows ? xr[d] / nrm : xr[d]) : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[(size_t)row * Dp + d] = h;
+    mid[(size_t)row * Dp + d] = m;
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) norms[row] = ss;
+}
+
+__global__ void row_norms_kernel(const float* __restrict__ x, int n, int D, float* __restrict__ norms) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  float ss = 0.f;
+  for (int d = lane; d < D; d += 32) { float v = x[(size_t)row * D + d]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) norms[row] = ss;
+}
+
+__global__ void sel_init_kernel(SelState s, int rows, int first_chunk) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) { s.tau[r] = INFINITY; s.cnt[r] = first_chunk; }
+  if (r == 0) *s.overflow = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cross-check path: 64x64 tile, 16x16 threads, 4x4 micro-tile, fp32 FFMA in ascending d order.
+__global__ void __launch_bounds__(256)
+knn_simt_filter_kernel(const float* __restrict__ q, const float* __restrict__ r, const float* __restrict__ qn,
+                       const float* __restrict__ rn, int rows, int D, int c0, int c1, int first_round, SelState sel) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row0 = blockIdx.y * 64, col0 = c0 + blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < D; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int rr = i >> 4, kk = i & 15;
+      int gr = row0 + rr, gc = col0 + rr, gk = k0 + kk;
+      As[kk][rr] = (gr < rows && gk < D) ? q[(size_t)gr * D + gk] : 0.f;
+      Bs[kk][rr] = (gc < c1 && gk < D) ? r[(size_t)gc * D + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = row0 + ty * 4 + i;
+    if (row >= rows) continue;
+    const float qnr = qn[row], tau = sel.tau[row];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = col0 + tx * 4 + j;
+      if (col >= c1) continue;
+      const float d2 = make_d2(qnr, rn[col], acc[i][j]);
+      if (first_round) {
+        sel.cand_d2[(size_t)row * kCandCap + (col - c0)] = d2;
+        sel.cand_idx[(size_t)row * kCandCap + (col - c0)] = col;
+      } else if (d2 <= tau) {
+        cand_append(sel, row, col, d2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a): mbarrier, TMA, tcgen05
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug must not hang the GPU box; trap instead (reported as a CUDA error).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a bug, not a wait
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+// start>>4 [0,14) | LBO>>4 [16,30) (ignored for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B (8 rows x 128 B)
+// | version=1 [46,48) | layout_type=SWIZZLE_128B(2) [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                                ((uint32_t)(kTileM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------------
+// Persistent tcgen05 all-pairs + filter kernel.
+// grid = min(#tiles, #SMs); tile t -> (col_tile = t / n_row_tiles, row_tile = t % n_row_tiles) so that
+// concurrently running CTAs share the same reference tile through L2 and the bank streams from HBM once.
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qmid,
+                     const __grid_constant__ CUtensorMap map_rhi, const __grid_constant__ CUtensorMap map_rmid,
+                     const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int rows, int c0, int c1,
+                     int num_kb, int first_round, SelState sel) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // stage layout: [Qhi 16K][Qmid 16K][Rhi 32K][Rmid 32K]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_full = smem_u32(bars + 0);        // [kStages]
+  const uint32_t bar_empty = smem_u32(bars + 2);       // [kStages]
+  const uint32_t bar_tfull = smem_u32(bars + 4);       // [2] accumulator ready
+  const uint32_t bar_tempty = smem_u32(bars + 6);      // [2] accumulator drained
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_row_tiles = (rows + kTileM - 1) / kTileM;
+  const int n_col_tiles = (c1 - c0 + kTileN - 1) / kTileN;
+  const int n_tiles = n_row_tiles * n_col_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns = two 128x256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rhi) : "memory");
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
+        const int qy = q_row0 + rt * kTileM, ry = c0 + ct * kTileN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
+          tma_load_2d(sbase, &map_qhi, bar_full + 8 * stage, kb * kTileK, qy);
+          tma_load_2d(sbase + 16384, &map_qmid, bar_full + 8 * stage, kb * kTileK, qy);
+          tma_load_2d(sbase + 32768, &map_rhi, bar_full + 8 * stage, kb * kTileK, ry);
+          tma_load_2d(sbase + 65536, &map_rmid, bar_full + 8 * stage, kb * kTileK, ry);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, use = it >> 1;
+        mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kTileN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
+          const uint64_t qhi = umma_desc_sw128(sbase), qmid = umma_desc_sw128(sbase + 16384);
+          const uint64_t rhi = umma_desc_sw128(sbase + 32768), rmid = umma_desc_sw128(sbase + 65536);
+#pragma unroll
+          for (int kk = 0; kk < kTileK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 B along K inside the swizzle row
+            tc_mma_bf16(d_tmem, qhi + adv, rhi + adv, kIdescBf16, (kb | kk) != 0);
+            tc_mma_bf16(d_tmem, qhi + adv, rmid + adv, kIdescBf16, 1);
+            tc_mma_bf16(d_tmem, qmid + adv, rhi + adv, kIdescBf16, 1);
+          }
+          tc_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(bar_tfull + 8 * buf);      // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    const int quarter = warp & 3;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
+      const uint32_t buf = it & 1, use = it >> 1;
+      const int row = rt * kTileM + quarter * 32 + lane;
+      const bool row_ok = row < rows;
+      const float qnr = row_ok ? qn[q_row0 + row] : 0.f;
+      const float tau = row_ok ? sel.tau[row] : -1.f;
+      const int colbase = c0 + ct * kTileN;
+      mbar_wait(bar_tfull + 8 * buf, use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN;
+#pragma unroll 1
+      for (int c = 0; c < kTileN; c += 32) {
+        uint32_t v[32];
+        tc_ld32(taddr + c, v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = colbase + c + j;
+            if (col < c1) {
+              const float d2 = make_d2(qnr, __ldg(rn + col), __uint_as_float(v[j]));
+              if (first_round) {
+                sel.cand_d2[(size_t)row * kCandCap + (col - c0)] = d2;
+                sel.cand_idx[(size_t)row * kCandCap + (col - c0)] = col;
+              } else if (d2 <= tau) {
+                cand_append(sel, row, col, d2);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-row candidate refinement (one CTA per row).  key = (d2 bits << 32) | idx ; d2 >= +0 so the
+// unsigned order of the bits is the float order; ascending key == (d2 asc, idx asc).
+__global__ void __launch_bounds__(256)
+knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int q_row0, float* __restrict__ d2_out,
+                  long long* __restrict__ idx_out) {
+  __shared__ unsigned long long keys[kCandCap];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  int n = sel.cnt[row];
+  if (n > kCandCap) n = kCandCap;
+  if (!final_pass && n <= k) return;
+  int P = 1;
+  while (P < n) P <<= 1;
+  const float* cd = sel.cand_d2 + (size_t)row * kCandCap;
+  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  for (int i = tid; i < P; i += 256)
+    keys[i] = i < n ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | (unsigned)ci[i]) : ~0ull;
+  __syncthreads();
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          if ((a > b) == ((i & kk) == 0)) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!final_pass) {
+    float* wd = sel.cand_d2 + (size_t)row * kCandCap;
+    int* wi = sel.cand_idx + (size_t)row * kCandCap;
+    for (int i = tid; i < k; i += 256) {
+      wd[i] = __uint_as_float((unsigned)(keys[i] >> 32));
+      wi[i] = (int)(unsigned)keys[i];
+    }
+    if (tid == 0) {
+      sel.cnt[row] = k;
+      sel.tau[row] = __uint_as_float((unsigned)(keys[k - 1] >> 32));
+    }
+  } else {
+    const size_t o = (size_t)(q_row0 + row) * k;
+    for (int i = tid; i < k; i += 256) {
+      if (i < n) {
+        d2_out[o + i] = __uint_as_float((unsigned)(keys[i] >> 32));
+        idx_out[o + i] = row_offset + (long long)(unsigned)keys[i];
+      } else {
+        d2_out[o + i] = INFINITY;
+        idx_out[o + i] = -1;
+      }
+    }
+  }
+}
+
+// k-way merge of G per-shard lists: [G][Nq][k] -> [Nq][k]
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const float* __restrict__ d2p, const long long* __restrict__ idxp, int G, int Nq, int k,
+                  float* __restrict__ d2_out, long long* __restrict__ idx_out) {
+  extern __shared__ unsigned long long mkeys[];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int n = G * k;
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = tid; i < P; i += 256) {
+    unsigned long long key = ~0ull;
+    if (i < n) {
+      const int g = i / k, j = i - g * k;
+      const size_t o = ((size_t)g * Nq + row) * k + j;
+      const long long id = idxp[o];
+      float d = d2p[o];
+      if (id >= 0) key = ((unsigned long long)__float_as_uint(d > 0.f ? d : 0.f) << 32) | (unsigned)id;
+    }
+    mkeys[i] = key;
+  }
+  __syncthreads();
+  for (int kk = 2; kk <= P; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = mkeys[i], b = mkeys[ixj];
+          if ((a > b) == ((i & kk) == 0)) { mkeys[i] = b; mkeys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += 256) {
+    const unsigned long long key = i < P ? mkeys[i] : ~0ull;
+    const size_t o = (size_t)row * k + i;
+    if (key != ~0ull) {
+      d2_out[o] = __uint_as_float((unsigned)(key >> 32));
+      idx_out[o] = (long long)(unsigned)key;
+    } else {
+      d2_out[o] = INFINITY;
+      idx_out[o] = -1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+struct KnnLayout {
+  SelState sel; float* qn; float* rn; int* flags; size_t total;
+};
+static KnnLayout carve_knn(void* ws, int Nq, int Nr) {
+  Carver c(ws);
+  KnnLayout L;
+  const int rows = Nq < kQueryBlock ? Nq : kQueryBlock;
+  L.sel.tau = c.take<float>(rows);
+  L.sel.cnt = c.take<int>(rows);
+  L.sel.cand_d2 = c.take<float>((size_t)rows * kCandCap);
+  L.sel.cand_idx = c.take<int>((size_t)rows * kCandCap);
+  L.sel.overflow = c.take<int>(1);
+  L.qn = c.take<float>(Nq);   // SIMT path only
+  L.rn = c.take<float>(Nr);   // SIMT path only
+  L.flags = c.take<int>((Nq + kQueryBlock - 1) / kQueryBlock + 1);
+  L.total = c.total();
+  return L;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+static int make_map(CUtensorMap* m, const __nv_bfloat16* base, int n, int Dp, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SEGVLAD_ECUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)n};
+  cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SEGVLAD_ECUDA; }
+  return SEGVLAD_OK;
+}
+
+// chunk schedule: first chunk fills the buffer, later chunks grow with the number of refs already seen
+static int next_chunk(int seen, int k, int Nr, bool safe) {
+  long long c;
+  if (seen == 0) c = kCandCap;
+  else if (safe) c = kCandCap - k;
+  else c = (long long)((double)seen * (double)(kCandCap - k) / ((double)k * 2.5));
+  c = c / kTileN * kTileN;
+  if (c < kTileN) c = kTileN;
+  if (c > Nr - seen) c = Nr - seen;
+  return (int)c;
+}
+
+struct TcArgs { BankView q, r; CUtensorMap mqhi, mqmid, mrhi, mrmid; int num_sms; };
+struct SimtArgs { const float* q; const float* r; };
+
+static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLayout& L, int q_row0, int rows, int Nr,
+                     int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
+                     cudaStream_t st) {
+  int seen = 0;
+  const int first = next_chunk(0, k, Nr, safe);
+  sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, first);
+  SV_CHECK_LAUNCH();
+  while (seen < Nr) {
+    const int chunk = next_chunk(seen, k, Nr, safe);
+    const int c0 = seen, c1 = seen + chunk;
+    const int first_round = seen == 0;
+    if (tc) {
+      const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
+      const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
+      const size_t smem = kStages * kStageBytes + 1024 + 256;
+      knn_tc_filter_kernel<<<grid, kTcThreads, smem, st>>>(ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid, ta->q.norms,
+                                                          ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK,
+                                                          first_round, L.sel);
+    } else {
+      dim3 grid((chunk + 63) / 64, (rows + 63) / 64);
+      knn_simt_filter_kernel<<<grid, 256, 0, st>>>(sa->q + (size_t)q_row0 * D, sa->r, L.qn + q_row0, L.rn, rows, D, c0,
+                                                   c1, first_round, L.sel);
+    }
+    SV_CHECK_LAUNCH();
+    seen = c1;
+    const int final_pass = seen >= Nr;
+    knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, k, final_pass, row_offset, q_row0, d2_out, idx_out);
+    SV_CHECK_LAUNCH();
+  }
+  return SEGVLAD_OK;
+}
+
+static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, int D, int k, long long row_offset,
+                      float* d2_out, long long* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  SV_REQUIRE(Nq >= 0 && Nr >= 0 && D > 0, "knn: bad shape");
+  SV_REQUIRE(k > 0 && k <= kMaxK, "knn: k must be in [1, %d] (got %d)", kMaxK, k);
+  if (Nq == 0) return SEGVLAD_OK;
+  KnnLayout L = carve_knn(workspace, Nq, Nr);
+  if (!workspace || workspace_bytes < L.total) {
+    set_error("knn: workspace %zu < required %zu", workspace_bytes, L.total);
+    return SEGVLAD_EWORKSPACE;
+  }
+  const int n_blocks = (Nq + kQueryBlock - 1) / kQueryBlock;
+  if (Nr == 0) {  // nothing to search: pad like faiss
+    for (int b = 0; b < n_blocks; ++b) {
+      const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
+      sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, 0);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, k, 1, row_offset, q0, d2_out, idx_out);
+      SV_CHECK_LAUNCH();
+    }
+    return SEGVLAD_OK;
+  }
+  if (!tc) {
+    row_norms_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(sa->q, Nq, D, L.qn);
+    row_norms_kernel<<<(Nr + 7) / 8, 256, 0, st>>>(sa->r, Nr, D, L.rn);
+    SV_CHECK_LAUNCH();
+  }
+  for (int b = 0; b < n_blocks; ++b) {
+    const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
+    int rc = run_block(tc, ta, sa, L, q0, rows, Nr, D, k, row_offset, false, d2_out, idx_out, st);
+    if (rc) return rc;
+    SV_CHECK_CUDA(cudaMemcpyAsync(L.flags + b, L.sel.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  }
+  int hflags[64];
+  SV_REQUIRE(n_blocks <= 64, "knn: too many query blocks (%d)", n_blocks);
+  SV_CHECK_CUDA(cudaMemcpyAsync(hflags, L.flags, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st));
+  SV_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int b = 0; b < n_blocks; ++b) {
+    if (!hflags[b]) continue;
+    const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
+    int rc = run_block(tc, ta, sa, L, q0, rows, Nr, D, k, row_offset, true, d2_out, idx_out, st);
+    if (rc) return rc;
+    int f = 0;
+    SV_CHECK_CUDA(cudaMemcpyAsync(&f, L.sel.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SV_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (f) { set_error("knn: candidate overflow in the conservative schedule (internal error)"); return SEGVLAD_EOVERFLOW; }
+  }
+  return SEGVLAD_OK;
+}
+
+}  // namespace segvlad
+
+using namespace segvlad;
+
+extern "C" size_t segvlad_bank_bytes(int n, int D) {
+  if (n < 0 || D <= 0) return 0;
+  Carver c(nullptr);
+  const int Dp = padded_dim(D);
+  c.take<__nv_bfloat16>((size_t)n * Dp);
+  c.take<__nv_bfloat16>((size_t)n * Dp);
+  c.take<float>(n);
+  return c.total() + 256;
+}
+
+extern "C" int segvlad_bank_prepare(const float* x, int n, int D, void* bank, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(n >= 0 && D > 0 && bank, "bank_prepare: bad arguments");
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(bank) & 255) == 0, "bank_prepare: bank must be 256-byte aligned");
+  if (n == 0) return SEGVLAD_OK;
+  BankView v = bank_view(bank, n, D);
+  bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, v.Dp, const_cast<__nv_bfloat16*>(v.hi),
+                                                   const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms));
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+extern "C" int segvlad_bank_prepare_f64(const double* x, int n, int D, int normalize_rows, void* bank, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(n >= 0 && D > 0 && bank, "bank_prepare_f64: bad arguments");
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(bank) & 255) == 0, "bank_prepare_f64: bank must be 256-byte aligned");
+  if (n == 0) return SEGVLAD_OK;
+  BankView v = bank_view(bank, n, D);
+  bank_prepare_f64_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, v.Dp, normalize_rows, const_cast<__nv_bfloat16*>(v.hi),
+                                                       const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms));
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+extern "C" size_t segvlad_knn_workspace_bytes(int Nq, int Nr, int D, int k) {
+  (void)D; (void)k;
+  if (Nq <= 0 || Nr < 0) return 256;
+  return carve_knn(nullptr, Nq, Nr).total;
+}
+
+extern "C" int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D, int k,
+                           float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(D > 0, "knn: bad D");
+  TcArgs ta;
+  if (Nq > 0 && Nr > 0) {
+    ta.q = bank_view(qbank, Nq, D);
+    ta.r = bank_view(rbank, Nr, D);
+    int rc;
+    if ((rc = make_map(&ta.mqhi, ta.q.hi, Nq, ta.q.Dp, kTileM))) return rc;
+    if ((rc = make_map(&ta.mqmid, ta.q.mid, Nq, ta.q.Dp, kTileM))) return rc;
+    if ((rc = make_map(&ta.mrhi, ta.r.hi, Nr, ta.r.Dp, kTileN))) return rc;
+    if ((rc = make_map(&ta.mrmid, ta.r.mid, Nr, ta.r.Dp, kTileN))) return rc;
+    int dev = 0;
+    SV_CHECK_CUDA(cudaGetDevice(&dev));
+    SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kStages * kStageBytes + 1024 + 256));
+  }
+  return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
+                    workspace, workspace_bytes, st);
+}
+
+extern "C" int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, int64_t row_offset, int D, int k,
+                                float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
+                                void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SimtArgs sa{q, r};
+  return knn_driver(false, nullptr, &sa, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
+                    workspace, workspace_bytes, st);
+}
+
+extern "C" int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, int Nq, int k, float* d2_out,
+                                  int64_t* idx_out, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(G > 0 && Nq >= 0 && k > 0, "merge_topk: bad shape");
+  SV_REQUIRE((long long)G * k <= 16384, "merge_topk: G*k must be <= 16384 (got %lld)", (long long)G * k);
+  if (Nq == 0) return SEGVLAD_OK;
+  int P = 1;
+  while (P < G * k) P <<= 1;
+  const size_t smem = (size_t)P * 8;
+  SV_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+  merge_topk_kernel<<<Nq, 256, smem, st>>>(d2_parts, reinterpret_cast<const long long*>(idx_parts), G, Nq, k, d2_out,
+                                           reinterpret_cast<long long*>(idx_out));
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}

@@ -1,0 +1,250 @@
+"""Device-resident API of the SegVLAD engine: thin torch-tensor wrappers over the C ABI.
+
+Every function takes/returns CUDA tensors, launches on torch's current stream and allocates its
+workspace from torch's caching allocator (the library itself never allocates).  PyTorch is plumbing
+here (device memory, streams); all arithmetic of the hot path happens inside libsegvlad.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import OUT_F32, OUT_F64, TOKENS_DN, TOKENS_ND, TOKENS_PRENORMALIZED, check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise ValueError("segvlad engine expects CUDA tensors (no CPU fallback)")
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------------------------
+# membership
+# --------------------------------------------------------------------------------------------
+def mask_to_membership(masks_u8: torch.Tensor, H: int, W: int, patch: int = 14) -> torch.Tensor:
+    """[S,Hm,Wm] uint8/bool CUDA pixel masks -> [S, ceil(N/32)] int32 membership bitmask
+    (func_vpr.py:1088-1092 semantics; kernel segvlad_mask_to_membership)."""
+    _need_cuda(masks_u8)
+    m = masks_u8.to(torch.uint8).contiguous()
+    S, Hm, Wm = m.shape
+    N = (H // patch) * (W // patch)
+    bits = torch.zeros((S, (N + 31) // 32), dtype=torch.int32, device=m.device)
+    check(lib().segvlad_mask_to_membership(_ptr(m), S, Hm, Wm, H, W, patch, _ptr(bits), _stream()),
+          "segvlad_mask_to_membership")
+    return bits
+
+
+def pack_membership(member_bool: torch.Tensor) -> torch.Tensor:
+    """[S,N] bool CUDA -> [S, ceil(N/32)] int32 bit rows (format conversion for callers that already hold
+    the reference's `mask_idx` tensor, e.g. the vlad_single drop-in)."""
+    S, N = member_bool.shape
+    Wd = (N + 31) // 32
+    pad = torch.zeros((S, Wd * 32), dtype=torch.int64, device=member_bool.device)
+    pad[:, :N] = member_bool.to(torch.int64)
+    w = (pad.view(S, Wd, 32) << torch.arange(32, device=member_bool.device, dtype=torch.int64)).sum(-1)
+    w = w - ((w >= 2 ** 31).to(torch.int64) << 32)      # reinterpret the uint32 word as int32
+    return w.to(torch.int32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# aggregation
+# --------------------------------------------------------------------------------------------
+def aggregate_batch(tokens: torch.Tensor, N: int, D: int, token_layout: int, centers: torch.Tensor,
+                    member_bits: torch.Tensor, seg_counts: Sequence[int],
+                    adj: Optional[Sequence[Optional[torch.Tensor]]] = None, out_dtype=torch.float64,
+                    return_labels: bool = False):
+    """Batched per-(Super)Segment VLAD.  tokens: n_images*N*D fp32 (layout per `token_layout`);
+    member_bits [S_total, ceil(N/32)] int32; seg_counts: segments per image; adj: per-image [S_i,S_i]
+    bool/uint8 CUDA tensors or None (order 0).  Returns [S_total, K*D] (+ labels [n_images, N])."""
+    _need_cuda(tokens, centers, member_bits)
+    B = len(seg_counts)
+    K = centers.shape[0]
+    dev = tokens.device
+    tokens = tokens.contiguous().float()
+    centers = centers.contiguous().float()
+    member_bits = member_bits.contiguous()
+    seg_off = np.zeros(B + 1, dtype=np.int32)
+    seg_off[1:] = np.cumsum(np.asarray(seg_counts, dtype=np.int64))
+    S_total = int(seg_off[-1])
+    assert tokens.numel() == B * N * D, "tokens size mismatch"
+    assert member_bits.shape == (S_total, (N + 31) // 32), "member_bits shape mismatch"
+    adj_flat = None
+    if adj is not None and any(a is not None for a in adj):
+        parts = []
+        for b in range(B):
+            Si = int(seg_counts[b])
+            a = adj[b]
+            if a is None:
+                a = torch.eye(Si, dtype=torch.uint8, device=dev)
+            assert a.shape == (Si, Si), "adjacency shape mismatch"
+            parts.append(a.to(device=dev, dtype=torch.uint8).reshape(-1))
+        adj_flat = torch.cat(parts).contiguous() if parts else None
+    odt = OUT_F64 if out_dtype == torch.float64 else OUT_F32
+    out = torch.empty((S_total, K * D), dtype=torch.float64 if odt == OUT_F64 else torch.float32, device=dev)
+    labels = torch.empty((B, N), dtype=torch.int32, device=dev) if return_labels else None
+    nbytes = lib().segvlad_aggregate_workspace_bytes(B, N, D, K, S_total)
+    ws = _ws(nbytes, dev)
+    check(lib().segvlad_aggregate_batch(_ptr(tokens), B, N, D, token_layout, _ptr(centers), K, _ptr(member_bits),
+                                        seg_off.ctypes.data_as(C.c_void_p), _ptr(adj_flat), _ptr(out), odt,
+                                        _ptr(labels), _ptr(ws), ws.numel(), _stream()),
+          "segvlad_aggregate_batch")
+    return (out, labels) if return_labels else out
+
+
+def aggregate_residuals(residuals: torch.Tensor, labels: torch.Tensor, N: int, D: int, K: int,
+                        member_bits: torch.Tensor, seg_counts: Sequence[int],
+                        adj: Optional[Sequence[Optional[torch.Tensor]]] = None, out_dtype=torch.float64):
+    """Inner aggregation stage on caller-provided residual rows [n_images*N, D] and labels
+    (vlad_matmuls_per_cluster semantics, func_vpr.py:1181-1210)."""
+    _need_cuda(residuals, labels, member_bits)
+    B = len(seg_counts)
+    dev = residuals.device
+    residuals = residuals.contiguous().float()
+    labels = labels.contiguous().to(torch.int32)
+    seg_off = np.zeros(B + 1, dtype=np.int32)
+    seg_off[1:] = np.cumsum(np.asarray(seg_counts, dtype=np.int64))
+    S_total = int(seg_off[-1])
+    adj_flat = None
+    if adj is not None and any(a is not None for a in adj):
+        parts = []
+        for b in range(B):
+            Si = int(seg_counts[b])
+            a = adj[b] if adj[b] is not None else torch.eye(Si, dtype=torch.uint8, device=dev)
+            parts.append(a.to(device=dev, dtype=torch.uint8).reshape(-1))
+        adj_flat = torch.cat(parts).contiguous()
+    odt = OUT_F64 if out_dtype == torch.float64 else OUT_F32
+    out = torch.empty((S_total, K * D), dtype=torch.float64 if odt == OUT_F64 else torch.float32, device=dev)
+    ws = _ws(lib().segvlad_aggregate_workspace_bytes(B, N, D, K, S_total), dev)
+    check(lib().segvlad_aggregate_residuals(_ptr(residuals), _ptr(labels), B, N, D, K, _ptr(member_bits.contiguous()),
+                                            seg_off.ctypes.data_as(C.c_void_p), _ptr(adj_flat), _ptr(out), odt,
+                                            _ptr(ws), ws.numel(), _stream()), "segvlad_aggregate_residuals")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# matching
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Bank:
+    """Kernel-ready resident form of an [n, D] descriptor matrix (bf16 hi/mid planes + norms)."""
+    buf: torch.Tensor
+    n: int
+    D: int
+
+    @staticmethod
+    def prepare(x: torch.Tensor) -> "Bank":
+        _need_cuda(x)
+        x = x.contiguous().float()
+        n, D = x.shape
+        buf = _ws(lib().segvlad_bank_bytes(n, D), x.device)
+        check(lib().segvlad_bank_prepare(_ptr(x), n, D, _ptr(buf), _stream()), "segvlad_bank_prepare")
+        return Bank(buf, n, D)
+
+    @staticmethod
+    def prepare_f64(x: torch.Tensor, normalize_rows: bool = False) -> "Bank":
+        """fp64 descriptors (the reference's segFtVLAD dtype): optional normalizeFeat in fp64, fp32 cast, split."""
+        _need_cuda(x)
+        x = x.contiguous().double()
+        n, D = x.shape
+        buf = _ws(lib().segvlad_bank_bytes(n, D), x.device)
+        check(lib().segvlad_bank_prepare_f64(_ptr(x), n, D, int(normalize_rows), _ptr(buf), _stream()),
+              "segvlad_bank_prepare_f64")
+        return Bank(buf, n, D)
+
+
+def knn(q: Bank, r: Bank, k: int, row_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """tcgen05 all-pairs squared-L2 + fused threshold filter + top-k.  Returns (d2 [Nq,k] fp32 ascending,
+    idx [Nq,k] int64 global rows; (+inf,-1) padded)."""
+    assert q.D == r.D
+    dev = q.buf.device
+    d2 = torch.empty((q.n, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+    ws = _ws(lib().segvlad_knn_workspace_bytes(q.n, r.n, q.D, k), dev)
+    check(lib().segvlad_knn(_ptr(q.buf), q.n, _ptr(r.buf), r.n, int(row_offset), q.D, k, _ptr(d2), _ptr(idx),
+                            _ptr(ws), ws.numel(), _stream()), "segvlad_knn")
+    return d2, idx
+
+
+def knn_simt(q: torch.Tensor, r: torch.Tensor, k: int, row_offset: int = 0):
+    """fp32 FFMA cross-check path (same selection machinery, no tensor cores)."""
+    _need_cuda(q, r)
+    q = q.contiguous().float()
+    r = r.contiguous().float()
+    dev = q.device
+    d2 = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev)
+    idx = torch.empty((q.shape[0], k), dtype=torch.int64, device=dev)
+    ws = _ws(lib().segvlad_knn_workspace_bytes(q.shape[0], r.shape[0], q.shape[1], k), dev)
+    check(lib().segvlad_knn_simt(_ptr(q), q.shape[0], _ptr(r), r.shape[0], int(row_offset), q.shape[1], k,
+                                 _ptr(d2), _ptr(idx), _ptr(ws), ws.numel(), _stream()), "segvlad_knn_simt")
+    return d2, idx
+
+
+def merge_topk(d2_parts: torch.Tensor, idx_parts: torch.Tensor):
+    """[G,Nq,k] per-shard lists -> merged [Nq,k] ((d2, idx) ascending)."""
+    _need_cuda(d2_parts, idx_parts)
+    G, Nq, k = d2_parts.shape
+    d2_parts = d2_parts.contiguous().float()
+    idx_parts = idx_parts.contiguous().to(torch.int64)
+    d2 = torch.empty((Nq, k), dtype=torch.float32, device=d2_parts.device)
+    idx = torch.empty((Nq, k), dtype=torch.int64, device=d2_parts.device)
+    check(lib().segvlad_merge_topk(_ptr(d2_parts), _ptr(idx_parts), G, Nq, k, _ptr(d2), _ptr(idx), _stream()),
+          "segvlad_merge_topk")
+    return d2, idx
+
+
+# --------------------------------------------------------------------------------------------
+# vote
+# --------------------------------------------------------------------------------------------
+@dataclass
+class VoteResult:
+    preds: torch.Tensor            # [n_qimg, n_pred] int32, -1 padded
+    pred_scores: torch.Tensor      # [n_qimg, n_pred] fp64
+    scores: Optional[torch.Tensor]  # [n_qimg, n_rimg] fp64 (dense) or None
+    counts: Optional[torch.Tensor]  # [n_qimg, n_rimg] int32 (dense) or None
+    minmax: torch.Tensor           # [2] fp32
+
+
+def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, rseg_to_rimg: torch.Tensor,
+         n_rimg: int, n_pred: int = 5, k_vote: int = 50, sims_is_d2: bool = False, dense: bool = False,
+         max_segs: Optional[int] = None) -> VoteResult:
+    """Similarity-weighted segment->image vote (get_matches 'max_seg_topk_wt_borda_Im' semantics) + hit
+    counts.  matches/sims: [Nq, ld] int64 / fp32 (first k_vote columns used); qimg_offsets [n_qimg+1] int32."""
+    _need_cuda(matches, sims, qimg_offsets, rseg_to_rimg)
+    assert matches.dtype == torch.int64 and sims.dtype == torch.float32
+    assert matches.stride(1) == 1 and sims.stride(1) == 1 and matches.stride(0) == sims.stride(0)
+    Nq, ld = matches.shape[0], matches.stride(0) if matches.shape[0] > 1 else matches.shape[1]
+    k_vote = min(k_vote, matches.shape[1])
+    dev = matches.device
+    qimg_offsets = qimg_offsets.to(device=dev, dtype=torch.int32).contiguous()
+    rseg_to_rimg = rseg_to_rimg.to(device=dev, dtype=torch.int32).contiguous()
+    n_qimg = qimg_offsets.numel() - 1
+    if max_segs is None:
+        max_segs = int((qimg_offsets[1:] - qimg_offsets[:-1]).max().item()) if n_qimg > 0 else 0
+    preds = torch.empty((n_qimg, n_pred), dtype=torch.int32, device=dev)
+    pscores = torch.empty((n_qimg, n_pred), dtype=torch.float64, device=dev)
+    scores = torch.empty((n_qimg, n_rimg), dtype=torch.float64, device=dev) if dense else None
+    counts = torch.empty((n_qimg, n_rimg), dtype=torch.int32, device=dev) if dense else None
+    mm = torch.empty(2, dtype=torch.float32, device=dev)
+    ws = _ws(lib().segvlad_vote_workspace_bytes(Nq, k_vote, n_qimg, max_segs), dev)
+    check(lib().segvlad_vote(_ptr(matches), _ptr(sims), ld, int(sims_is_d2), k_vote, Nq, _ptr(qimg_offsets), n_qimg,
+                             max_segs, _ptr(rseg_to_rimg), rseg_to_rimg.numel(), n_rimg, n_pred, _ptr(preds),
+                             _ptr(pscores), _ptr(scores), _ptr(counts), _ptr(mm), _ptr(ws), ws.numel(), _stream()),
+          "segvlad_vote")
+    return VoteResult(preds, pscores, scores, counts, mm)

@@ -1,0 +1,247 @@
+"""Drop-in mirror of the reference's `func_vpr` functions that sit on the SegVLAD hot path.
+
+Same names, argument meaning, return types and error behaviour as /root/reference/func_vpr.py, with the
+arithmetic running in libsegvlad.so on the B200 (no CPU fallback: a missing library or GPU raises).
+A driver written against the reference can do `from revisit_anything_b200 import func_vpr` and keep
+calling
+
+    seg_vlad_gpu_single / seg_vlad_gpu_single_img   (func_vpr.py:1065-1138)
+    vlad_single / vlad_matmuls_per_cluster          (func_vpr.py:1140-1210)
+    get_matches / weighted_borda_count              (func_vpr.py:61-243)
+    calc_recall, normalizeFeat, nbrMasksAGGFastSingle, getIdxSingleFast, preload_masks,
+    first_k_unique_indices                          (host-side helpers, kept on the host as in the reference)
+
+Batched, device-resident fast paths (no per-image D2H) live in `engine.py` / `place_rec_main.py`.
+"""
+from __future__ import annotations
+
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import TOKENS_DN, TOKENS_ND, TOKENS_PRENORMALIZED
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("segvlad: no CUDA device (the SegVLAD hot path has no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+# ------------------------------------------------------------------------------------------------
+# aggregation  (func_vpr.py:1065-1210)
+# ------------------------------------------------------------------------------------------------
+def _seg_vlad_from_tokens(dino_desc: torch.Tensor, segMask, c_centers, cfg, desc_dim, adj_mat, device_out=False):
+    dev = _dev()
+    H, W = cfg["desired_height"], cfg["desired_width"]
+    total = dino_desc.shape[2] * dino_desc.shape[3]
+    tok = dino_desc.reshape(desc_dim, total).to(dev, non_blocking=True)           # [D, N] reference layout
+    masks = torch.from_numpy(np.ascontiguousarray(np.asarray(segMask))).to(dev)     # [S, Hm, Wm] bool
+    S = masks.shape[0]
+    bits = engine.mask_to_membership(masks, H, W, 14)
+    if bits.shape[1] * 32 < total or (H // 14) * (W // 14) != total:
+        raise ValueError("token grid does not match cfg['desired_height'/'desired_width'] // 14")
+    adj = None if adj_mat is None else [adj_mat.to(dev)]
+    gd = engine.aggregate_batch(tok, total, desc_dim, TOKENS_DN, c_centers.to(dev), bits, [S], adj,
+                                out_dtype=torch.float64)
+    return gd if device_out else gd.cpu()
+
+
+def seg_vlad_gpu_single(ind, idx, desc_path_in, img_key, segMask, c_centers, cfg, desc_dim=1536, adj_mat=None):
+    """func_vpr.py:1065-1101.  `ind`/`idx` (pixel->patch lookup) are accepted and ignored: the lookup
+    rule (place_rec_main.py:187-194) is evaluated inside the membership kernel.  Returns a CPU fp64
+    tensor [S, K*desc_dim] like the reference."""
+    dino_desc = torch.from_numpy(desc_path_in[img_key]["ift_dino"][()])
+    return _seg_vlad_from_tokens(dino_desc, segMask, c_centers, cfg, desc_dim, adj_mat)
+
+
+def seg_vlad_gpu_single_img(ind, idx, dino_desc, img_key, segMask, c_centers, cfg, desc_dim=1536, adj_mat=None):
+    """func_vpr.py:1103-1138 (in-memory token tensor [1,D,dh,dw])."""
+    return _seg_vlad_from_tokens(dino_desc, segMask, c_centers, cfg, desc_dim, adj_mat)
+
+
+def vlad_single(query_descs, c_centers, idx, masks, adj_mat=None):
+    """func_vpr.py:1140-1179.  query_descs [N,D] (already normalised by the caller), masks [S,N] bool.
+    Returns (vlad [S,K*D] fp64 on the GPU, execution_time)."""
+    t0 = time.time()
+    dev = _dev()
+    x = query_descs.to(dev)
+    N, D = x.shape
+    bits = engine.pack_membership(masks.to(dev).bool())
+    adj = None if adj_mat is None else [adj_mat.to(dev)]
+    layout = TOKENS_ND | TOKENS_PRENORMALIZED
+    if x.stride(0) == 1 and x.stride(1) == N:      # the reference passes a permuted view of [D,N]
+        tok, layout = x.t(), TOKENS_DN | TOKENS_PRENORMALIZED
+    else:
+        tok = x.contiguous()
+    out = engine.aggregate_batch(tok, N, D, layout, c_centers.to(dev), bits, [masks.shape[0]], adj,
+                                 out_dtype=torch.float64)
+    return out, time.time() - t0
+
+
+def vlad_matmuls_per_cluster(num_c, masks, res, clus_labels, adjMat=None, device="cuda"):
+    """func_vpr.py:1181-1210.  masks [S,N] (0/1), res [N,D] residuals, clus_labels [N]; adjMat [S,S]."""
+    t0 = time.time()
+    if str(device).startswith("cpu"):
+        raise RuntimeError("segvlad: device='cpu' is not supported (no CPU fallback)")
+    dev = _dev()
+    res = res.to(dev)
+    N, D = res.shape
+    bits = engine.pack_membership(masks.to(dev) != 0)
+    adj = None if adjMat is None else [(adjMat.to(dev) != 0)]
+    out = engine.aggregate_residuals(res.float(), clus_labels.to(dev), N, D, int(num_c), bits, [masks.shape[0]], adj,
+                                     out_dtype=torch.float64)
+    return out, time.time() - t0
+
+
+# ------------------------------------------------------------------------------------------------
+# neighbourhood graph (CPU in the reference too: scipy Qhull)  func_vpr.py:1241-1245, 1309-1347
+# ------------------------------------------------------------------------------------------------
+def getNbrsDelaunay(tri, v):
+    indptr, indices = tri.vertex_neighbor_vertices
+    return [[v, u] for u in indices[indptr[v]:indptr[v + 1]]]
+
+
+def nbrMasksAGGFastSingle(masks_seg, order=1):
+    from scipy.spatial import Delaunay
+
+    S = len(masks_seg)
+    cords = np.array([np.array(np.nonzero(m)).mean(1)[::-1] for m in masks_seg])
+    adj = torch.zeros((S, S))
+    if S > 3:
+        tri = Delaunay(cords)
+        indptr, indices = tri.vertex_neighbor_vertices
+        for v in range(S):
+            adj[v, v] = 1
+            adj[v, torch.from_numpy(np.asarray(indices[indptr[v]:indptr[v + 1]], dtype=np.int64))] = 1
+        p = adj.clone()
+        for _ in range(order - 1):
+            p = p @ adj
+        return p.bool()
+    cols = [0, 1] if S > 1 else [0]
+    for v in range(S):
+        adj[v, cols] = 1
+    return adj.bool()
+
+
+# ------------------------------------------------------------------------------------------------
+# mask IO helpers (func_vpr.py:746-786)
+# ------------------------------------------------------------------------------------------------
+def _natural_key(s):
+    import re
+    return [int(t) if t.isdigit() else t for t in re.split(r"(\d+)", str(s))]
+
+
+def preload_masks(masks_in, image_key):
+    masks_path = f"{image_key}/masks/"
+    keys = sorted(masks_in[masks_path].keys(), key=_natural_key)
+    return [masks_in[masks_path + k]["segmentation"][()] for k in keys]
+
+
+def getIdxSingleFast(img_idx, masks_seg, minArea=400, returnMask=True):
+    """minArea is accepted and ignored, exactly like the reference (func_vpr.py:774-784)."""
+    n = len(masks_seg)
+    return np.array([img_idx] * n), list(range(n)), (list(masks_seg) if returnMask else [])
+
+
+# ------------------------------------------------------------------------------------------------
+# vote  (func_vpr.py:50-243)
+# ------------------------------------------------------------------------------------------------
+def first_k_unique_indices(ranked_indices, K):
+    seen = set()
+    out = []
+    for x in ranked_indices:
+        if x not in seen:
+            seen.add(x)
+            out.append(x)
+    return out[:K]
+
+
+def weighted_borda_count(*ranked_lists_with_scores):
+    """func_vpr.py:61-77 (host helper; get_matches below does the same accumulation on the GPU)."""
+    scores = {}
+    for ranked_list in ranked_lists_with_scores:
+        for index, score in ranked_list:
+            scores[index] = scores[index] + score if index in scores else score
+    return sorted(scores.keys(), key=lambda i: scores[i], reverse=True)
+
+
+def _ranges_to_offsets(segRangeQuery, n_img):
+    """segRangeQuery (list of index arrays) -> (row permutation or None, offsets[n_img+1])."""
+    lens = [len(segRangeQuery[i]) for i in range(n_img)]
+    off = np.zeros(n_img + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    cat = np.concatenate([np.asarray(segRangeQuery[i], dtype=np.int64) for i in range(n_img)]) if n_img else np.zeros(0, np.int64)
+    contiguous = cat.size == 0 or (np.array_equal(cat, np.arange(cat[0], cat[0] + cat.size)) and cat[0] == 0)
+    return (None if contiguous else cat), off
+
+
+def get_matches(matches, gt, sims, segRangeQuery, imIndsRef, n=1, method="max_sim"):
+    """func_vpr.py:80-243 for the methods the drivers use: "max_seg_topk_wt_borda_Im" (default of
+    recall_segloc), "max_seg_topk" and "max_seg".  Returns a list (per query image) of arrays of
+    reference-image ids, best first.  Methods whose reference branch calls undefined helpers raise."""
+    dev = _dev()
+    n_img = len(gt)
+    perm, off = _ranges_to_offsets(segRangeQuery, n_img)
+    m = torch.as_tensor(np.asarray(matches))
+    if method == "max_seg":
+        m = m.reshape(-1, 1)
+    m = m.to(dev).to(torch.int64)
+    if method in ("max_seg_topk", "max_seg"):
+        s = torch.zeros(m.shape, dtype=torch.float32, device=dev)
+    else:
+        s = torch.as_tensor(np.asarray(sims), dtype=torch.float32).to(dev)
+    if perm is not None:
+        pidx = torch.from_numpy(perm).to(dev)
+        m, s = m[pidx].contiguous(), s[pidx].contiguous()
+    else:
+        m, s = m.contiguous(), s.contiguous()
+    im = np.asarray(imIndsRef).astype(np.int64)
+    n_rimg = int(im.max()) + 1 if im.size else 1
+    rimg = torch.from_numpy(im).to(dev)
+    offs = torch.from_numpy(off.astype(np.int32)).to(dev)
+    if method == "max_seg_topk_wt_borda_Im":
+        res = engine.vote(m, s, offs, rimg, n_rimg, n_pred=n, k_vote=m.shape[1])
+        p = res.preds.cpu().numpy()
+        return [p[i][p[i] >= 0].astype(np.int64) for i in range(n_img)]
+    if method in ("max_seg_topk", "max_seg"):
+        res = engine.vote(m, s, offs, rimg, n_rimg, n_pred=1, k_vote=m.shape[1], dense=True)
+        c = res.counts.cpu().numpy()
+        out = []
+        for i in range(n_img):
+            ids = np.where(c[i] > 0)[0]
+            order = np.argsort(c[i][ids], kind="stable")   # (count desc, larger id first), see DESIGN.md
+            out.append(ids[np.flip(order[-n:])])
+        return out
+    raise NotImplementedError(f"get_matches: method {method!r} is not on the SegVLAD hot path "
+                              "(its reference branch is dead code or an analysis variant)")
+
+
+# ------------------------------------------------------------------------------------------------
+# metrics / misc host helpers (func_vpr.py:396-422, 1673-1676)
+# ------------------------------------------------------------------------------------------------
+def calc_recall(pred, gt, n, analysis=False):
+    recall = [0] * n
+    per_query = [0] * len(gt)
+    num_eval = 0
+    for i in range(len(gt)):
+        if len(gt[i]) == 0:
+            continue
+        num_eval += 1
+        for j in range(len(pred[i])):
+            hit = (pred[i] in gt[i]) if n == 1 and np.ndim(pred[i]) == 0 else (pred[i][j] in gt[i])
+            if hit:
+                recall[j] += 1
+                per_query[i] = 1
+                break
+    recalls = (np.cumsum(recall) / float(num_eval)).tolist()
+    return (recalls, per_query) if analysis else recalls
+
+
+def normalizeFeat(rfts):
+    rfts = np.array(rfts).reshape([len(rfts), -1])
+    rfts /= np.linalg.norm(rfts, axis=1)[:, None]
+    return rfts

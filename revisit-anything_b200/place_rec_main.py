@@ -1,0 +1,105 @@
+"""Drop-in mirror of the reference's `place_rec_main.py` hot path: `recall_segloc` (place_rec_main.py:44-96)
+plus the per-image descriptor loop (place_rec_main.py:244-355) as a batched, device-resident function.
+
+`recall_segloc` keeps the reference signature and return value (Recall@1..5 list).  The faiss
+IndexFlatL2 search is replaced by the tcgen05 kNN, `get_matches` by the vote kernel.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import engine, func_vpr
+from ._lib import TOKENS_DN
+
+K_SEARCH = 200   # place_rec_main.py:56,60
+K_VOTE = 50      # place_rec_main.py:78-79
+N_PRED = 5       # place_rec_main.py:84
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("segvlad: no CUDA device (the SegVLAD hot path has no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def search_and_vote(seg_ft_ref: torch.Tensor, seg_ft_qry: torch.Tensor, seg_range_q, im_inds_ref, n_qimg: int,
+                    pca: bool, k_search: int = K_SEARCH, k_vote: int = K_VOTE, n_pred: int = N_PRED):
+    """Device-resident core of recall_segloc: returns (d2 [Nq,k], idx [Nq,k], VoteResult)."""
+    dev = _dev()
+    f64 = seg_ft_ref.dtype == torch.float64
+    prep = (lambda x: engine.Bank.prepare_f64(x.to(dev), normalize_rows=pca)) if f64 or pca else \
+           (lambda x: engine.Bank.prepare(x.to(dev)))
+    rbank = prep(seg_ft_ref)
+    qbank = prep(seg_ft_qry)
+    d2, idx = engine.knn(qbank, rbank, k_search)
+    perm, off = func_vpr._ranges_to_offsets(seg_range_q, n_qimg)
+    m, s = idx, d2
+    if perm is not None:
+        pidx = torch.from_numpy(perm).to(dev)
+        m, s = idx[pidx].contiguous(), d2[pidx].contiguous()
+    im = np.asarray(im_inds_ref).astype(np.int64)
+    n_rimg = int(im.max()) + 1
+    res = engine.vote(m, s, torch.from_numpy(off.astype(np.int32)).to(dev), torch.from_numpy(im).to(dev), n_rimg,
+                      n_pred=n_pred, k_vote=k_vote, sims_is_d2=True)
+    return d2, idx, res
+
+
+def recall_segloc(workdir, dataset_name, experiment_config, experiment_name, segFtVLAD1, segFtVLAD2, gt, segRange2,
+                  imInds1, map_calculate, domain, save_results=True):
+    """place_rec_main.py:44-96.  segFtVLAD1/2: [Nr,D]/[Nq,D] tensors (CPU or CUDA; fp64 like the reference or
+    fp32); with experiment_config['pca'] rows are L2-normalised first (normalizeFeat).  The descriptor
+    dimension is taken from the data (the reference hard-codes 1024 / 49152 for faiss)."""
+    pca = bool(experiment_config["pca"])
+    d2, idx, res = search_and_vote(segFtVLAD1, segFtVLAD2, segRange2, imInds1, len(gt), pca)
+    if save_results:
+        out_folder = f"{workdir}/results/global/"
+        os.makedirs(f"{out_folder}/{experiment_name}", exist_ok=True)
+        pkl = f"{out_folder}/{experiment_name}/{dataset_name}_matches_sims_domain_{domain}__{experiment_config['results_pkl_suffix']}"
+        with open(pkl, "wb") as fh:   # same keys as the reference: 'sims' holds the squared distances
+            pickle.dump({"sims": d2.cpu().numpy(), "matches": idx.cpu().numpy()}, fh)
+        print(f"Results saved to {pkl}")
+    p = res.preds.cpu().numpy()
+    max_seg_preds = [p[i][p[i] >= 0].astype(np.int64) for i in range(len(gt))]
+    max_seg_recalls = func_vpr.calc_recall(max_seg_preds, gt, N_PRED)
+    print("VLAD + PCA Results \n ")
+    if map_calculate:
+        print("mAP calculation is outside the SegVLAD hot path (func_vpr.calculate_map): skipped")
+    print("Max Seg Logs: ", max_seg_recalls)
+    return max_seg_recalls
+
+
+def build_segment_descriptors(tokens: Sequence[torch.Tensor], masks: Sequence[Sequence[np.ndarray]],
+                              c_centers: torch.Tensor, cfg: dict, order: int, desc_dim: int = 1536,
+                              batch_images: int = 32, out_dtype=torch.float64, adjacency: Optional[Sequence] = None):
+    """Batched equivalent of the per-image loop place_rec_main.py:244-281 (reference side) / :309-352 (query
+    side): for every image, SuperSegment adjacency on the host (scipy, as in the reference), then ONE batched
+    aggregation launch per `batch_images` images; descriptors stay on the GPU.
+    tokens[i]: [1,D,dh,dw] fp32 (CPU or CUDA); masks[i]: list of [Hm,Wm] bool.
+    Returns (segFtVLAD [S_total, K*D] CUDA, imInds [S_total] int64 numpy)."""
+    dev = _dev()
+    H, W = cfg["desired_height"], cfg["desired_width"]
+    N = (H // 14) * (W // 14)
+    centers = c_centers.to(dev)
+    outs, im_inds = [], []
+    for b0 in range(0, len(tokens), batch_images):
+        b1 = min(len(tokens), b0 + batch_images)
+        tok = torch.stack([tokens[i].reshape(desc_dim, N) for i in range(b0, b1)]).to(dev, non_blocking=True)
+        counts, bits, adjs = [], [], []
+        for i in range(b0, b1):
+            ms = torch.from_numpy(np.ascontiguousarray(np.asarray(masks[i]))).to(dev)
+            bits.append(engine.mask_to_membership(ms, H, W, 14))
+            counts.append(len(masks[i]))
+            if adjacency is not None:
+                adjs.append(None if adjacency[i] is None else torch.as_tensor(adjacency[i]))
+            else:
+                adjs.append(func_vpr.nbrMasksAGGFastSingle(masks[i], order) if order else None)
+            im_inds.append(np.full(len(masks[i]), i, dtype=np.int64))
+        gd = engine.aggregate_batch(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
+                                    adjs if order else None, out_dtype=out_dtype)
+        outs.append(gd)
+    return torch.cat(outs), np.concatenate(im_inds)

@@ -1,0 +1,168 @@
+"""GPU parity of the aggregation path (C ABI through the drop-in functions) vs the golden vectors generated
+from the reference and vs the oracle.  Tolerance: 1e-5 relative on descriptors (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import segvlad_oracle as O
+from revisit_anything_b200 import engine, func_vpr, synth
+from revisit_anything_b200._lib import TOKENS_DN, TOKENS_ND
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-9
+AGG_CASES = ["agg_small_o2", "agg_small_o0", "agg_small_S3", "agg_unnorm_o1", "agg_realvocab_o3"]
+
+
+def _cmp(got, want):
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("name", AGG_CASES)
+def test_golden_reference_vectors(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = {"desired_height": int(g["H"]), "desired_width": int(g["W"])}
+    adj = torch.from_numpy(g["adj"]) if int(g["order"]) else None
+    D = g["centers"].shape[1]
+    gd = func_vpr.seg_vlad_gpu_single_img(None, None, torch.from_numpy(g["tokens"]), "img", list(g["masks"]),
+                                          torch.from_numpy(g["centers"]), cfg, desc_dim=D, adj_mat=adj)
+    assert gd.dtype == torch.float64 and not gd.is_cuda and gd.shape[0] == len(g["masks"])
+    _cmp(gd.numpy()[:, g["cols"]], g["vlad_cols"])
+    _cmp(np.linalg.norm(gd.numpy().reshape(gd.shape[0], 32, D), axis=2), g["row_block_norms"])
+
+
+def _image(seed, D, H, W, S, K=32, order=3):
+    dh, dw = H // 14, W // 14
+    centers = synth.make_centers(K, D, seed)
+    tokens = synth.make_tokens(D, dh, dw, seed, centers)
+    masks = synth.make_masks(S, H // 2, W // 2, seed)
+    adj = torch.from_numpy(O.neighbour_adjacency(masks, order)) if order else None
+    return centers, tokens, masks, adj
+
+
+def _check_against_oracle(seed, D, H, W, S, K, order, layout=TOKENS_DN, out_dtype=torch.float64):
+    centers, tokens, masks, adj = _image(seed, D, H, W, S, K, order)
+    cfg = {"desired_height": H, "desired_width": W}
+    want, labels, margin, member = O.seg_vlad_single_img(tokens, masks, centers, cfg, adj)
+    dev = torch.device("cuda")
+    N = (H // 14) * (W // 14)
+    bits = engine.mask_to_membership(torch.from_numpy(np.asarray(masks)).to(dev), H, W)
+    np.testing.assert_array_equal(engine.pack_membership(member.to(dev)).cpu().numpy(), bits.cpu().numpy())
+    tok = tokens.reshape(D, N).to(dev)
+    if layout == TOKENS_ND:
+        tok = tok.t().contiguous()
+    got, lab = engine.aggregate_batch(tok, N, D, layout, centers.to(dev), bits, [S], [adj] if adj is not None else None,
+                                      out_dtype=out_dtype, return_labels=True)
+    safe = margin.numpy() > 1e-5
+    np.testing.assert_array_equal(lab.cpu().numpy()[0][safe], labels.numpy()[safe])
+    assert safe.mean() > 0.99
+    if out_dtype == torch.float32:
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=1e-5, atol=1e-7)
+    else:
+        _cmp(got.cpu().numpy(), want.numpy())
+
+
+def test_17places_shape_vs_oracle():
+    # 640x480 -> N = 1530 tokens, D_t = 1536, K = 32, order-3 SuperSegments (config 1 shape)
+    _check_against_oracle(seed=101, D=1536, H=480, W=640, S=37, K=32, order=3)
+
+
+@pytest.mark.parametrize("D,K,order,S", [(768, 32, 3, 21), (768, 64, 1, 9), (256, 128, 2, 17), (64, 32, 0, 5)])
+def test_variants_vs_oracle(D, K, order, S):
+    _check_against_oracle(seed=7 + D + K, D=D, H=196, W=266, S=S, K=K, order=order)
+
+
+def test_token_major_layout_and_f32_output():
+    _check_against_oracle(seed=55, D=384, H=196, W=266, S=12, K=32, order=2, layout=TOKENS_ND)
+    _check_against_oracle(seed=56, D=384, H=196, W=266, S=12, K=32, order=2, out_dtype=torch.float32)
+
+
+def test_batched_images_ragged_segments_and_edge_cases():
+    # images with S = 1, 2, 3 (no Delaunay), an EMPTY mask row (zero vector), and a normal one, in one launch
+    dev = torch.device("cuda")
+    D, H, W, K = 128, 140, 182, 32
+    N = (H // 14) * (W // 14)
+    cfg = {"desired_height": H, "desired_width": W}
+    centers = synth.make_centers(K, D, 3)
+    toks, bits, counts, adjs, wants = [], [], [], [], []
+    for i, S in enumerate([1, 2, 3, 0, 11, 8]):
+        tokens = synth.make_tokens(D, H // 14, W // 14, 200 + i, centers)
+        masks = synth.make_masks(S, H // 2, W // 2, 300 + i) if S else []
+        if S == 8:
+            masks[2][:] = False                      # empty segment (cannot come out of SAM, must still work)
+            adj = None
+        else:
+            adj = torch.from_numpy(O.neighbour_adjacency(masks, 2)) if S else None
+        toks.append(tokens.reshape(D, N))
+        counts.append(S)
+        adjs.append(adj)
+        if S:
+            want, _, margin, member = O.seg_vlad_single_img(tokens, masks, centers, cfg, adj)
+            assert float(margin.min()) > 1e-5
+            wants.append(want.numpy())
+            bits.append(engine.mask_to_membership(torch.from_numpy(np.asarray(masks)).to(dev), H, W))
+    got = engine.aggregate_batch(torch.stack(toks).to(dev), N, D, TOKENS_DN, centers.to(dev), torch.cat(bits), counts,
+                                 adjs).cpu().numpy()
+    want = np.concatenate(wants)
+    _cmp(got, want)
+    empty_row = 1 + 2 + 3 + 11 + 2
+    assert np.abs(got[empty_row]).max() == 0.0
+
+
+def test_zero_residual_blocks_use_exact_row_norm():
+    # tokens exactly equal to (unit-norm) centres -> residual rows are exactly 0 -> block norm 0 although the
+    # cluster is populated: exercises the rownorm_fixup kernel (reference: F.normalize of an all-zero block)
+    dev = torch.device("cuda")
+    D, K, N, S = 64, 32, 96, 4
+    g = torch.Generator().manual_seed(0)
+    centers = torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1)
+    x = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    x[:20] = centers[3]
+    x[20:30] = centers[7]
+    member = torch.rand(S, N, generator=g) < 0.4
+    member[0, :30] = True
+    member[0, 30:] = False                           # segment 0 sees only zero-residual tokens -> all-zero row
+    lab0, _ = O.assign_labels(x, centers)
+    member[1] = (lab0 != 3) & (torch.rand(N, generator=g) < 0.5)
+    member[1, :20] = True                            # block (1, 3) is populated, but only by zero residuals
+    assert int(((lab0 == 3) & member[1]).sum()) == 20
+    want, labels, margin = O.vlad_single(x, centers, member, None)
+    out, _ = func_vpr.vlad_single(x.to(dev), centers.to(dev), None, member.to(dev), None)
+    _cmp(out.cpu().numpy(), want.numpy())
+    assert np.abs(out[0].cpu().numpy()).max() == 0.0
+
+
+def test_vlad_matmuls_per_cluster_dropin():
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(1)
+    N, D, K, S = 150, 96, 32, 10
+    res = torch.randn(N, D, generator=g)
+    labels = torch.randint(0, K, (N,), generator=g)
+    masks = (torch.rand(S, N, generator=g) < 0.2)
+    adj = (torch.rand(S, S, generator=g) < 0.3) | torch.eye(S, dtype=torch.bool)
+    want = O.aggregate_per_cluster(K, masks, res, labels, adj)
+    got, _ = func_vpr.vlad_matmuls_per_cluster(K, masks.double().to(dev), res.double().to(dev), labels.to(dev),
+                                              adjMat=adj.double().to(dev))
+    _cmp(got.cpu().numpy(), want.numpy())
+    with pytest.raises(RuntimeError):
+        func_vpr.vlad_matmuls_per_cluster(K, masks.double(), res.double(), labels, device="cpu")
+
+
+@pytest.mark.parametrize("H,W,Hm,Wm", [(480, 640, 240, 320), (480, 640, 480, 640), (224, 300, 100, 133)])
+def test_mask_to_membership_kernel(H, W, Hm, Wm):
+    masks = synth.make_masks(9, Hm, Wm, 5)
+    masks[0][:] = False
+    masks[0][-1, -1] = True                          # single pixel in the folded-in border cell
+    want = O.mask_to_patch_membership(masks, H, W)
+    dev = torch.device("cuda")
+    bits = engine.mask_to_membership(torch.from_numpy(np.asarray(masks)).to(dev), H, W)
+    np.testing.assert_array_equal(bits.cpu().numpy(),
+                                  engine.pack_membership(torch.from_numpy(want).to(dev)).cpu().numpy())
+
+
+def test_bad_arguments_raise():
+    dev = torch.device("cuda")
+    with pytest.raises(ValueError):
+        engine.aggregate_batch(torch.zeros(30 * 6, device=dev), 30, 6, TOKENS_DN, torch.zeros(32, 6, device=dev),
+                               torch.zeros((1, 1), dtype=torch.int32, device=dev), [1])   # D % 4 != 0
