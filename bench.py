@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- SegVLAD hot-path benchmark (contract: see the build prompt / DESIGN.md section "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+metric  : segments matched/sec = (query-seg x ref-seg pairs)/s over the whole match path
+          (bank prepare -> tcgen05 all-pairs + fused filter/top-k -> [all-gather + merge] -> vote)
+workload: BASELINE.json configs[1]: 10k query segs x 100k ref segs x 1536-D, k_search 200, k_vote 50,
+          100 query images x 100 segs, 1000 ref images x 100 segs, per GPU (weak scaling: every rank holds a
+          100k-row shard of the bank, queries replicated, one all-gather of the per-shard top-k).
+One "step" = one pass of that path.  `value` has inputs resident in HBM; `e2e` goes through the same public
+call with pinned HOST buffers (H2D of both descriptor matrices and D2H of the predictions inside the timed
+region).  --impl reference times the CPU restatement of the reference's path (faiss-style flat L2 + the
+reference's Python vote) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NQ, NR_PER_GPU, DM, K_SEARCH, K_VOTE, N_PRED = 10_000, 100_000, 1536, 200, 50, 5
+SEGS_PER_IMG = 100
+CPU_SAMPLE_Q = 2000          # bounded CPU sample: 2000 query segs (20 query images) x the full 100k-row bank
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (one sample every 200 ms)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(rank: int, device):
+    from revisit_anything_b200 import synth
+    q, _ = synth.make_descriptor_bank(NQ, 8, DM, seed=2, planted=0, device=device)            # same on all ranks
+    _, r = synth.make_descriptor_bank(8, NR_PER_GPU, DM, seed=100 + rank, planted=0, device=device)
+    # planted near-duplicates (cos ~ 0.9) so the top-k is not pure noise
+    g = torch.Generator(device=device).manual_seed(7 + rank)
+    qi = torch.randperm(NQ, generator=g, device=device)[:1000]
+    ri = torch.randperm(NR_PER_GPU, generator=g, device=device)[:1000]
+    mix = 0.9 * q[qi] + (1 - 0.81) ** 0.5 * r[ri]
+    r[ri] = mix / mix.norm(dim=1, keepdim=True)
+    return q.contiguous(), r.contiguous()
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference's path (place_rec_main.py:53-61 faiss flat-L2 restated with
+    blocked fp32 sgemm + top-k, then the reference's Python-loop vote func_vpr.py:207-224), all host threads."""
+    if rank != 0:
+        return
+    from oracle import segvlad_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    q, r = make_workload(0, "cpu")
+    qs = q[:CPU_SAMPLE_Q].numpy()
+    rn = r.numpy()
+    n_img = CPU_SAMPLE_Q // SEGS_PER_IMG
+    seg_range = [np.arange(i * SEGS_PER_IMG, (i + 1) * SEGS_PER_IMG) for i in range(n_img)]
+    im_inds_ref = (np.arange(NR_PER_GPU) // SEGS_PER_IMG).astype(np.int64)
+
+    def step():
+        D2, I = O.flat_l2_search_fast(qs, rn, K_SEARCH)
+        sims, matches = O.sims_from_d2(D2, I, K_VOTE)
+        return O.get_matches_wt_borda(matches, n_img, sims, seg_range, im_inds_ref, n=N_PRED)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    pairs = CPU_SAMPLE_Q * NR_PER_GPU
+    val = pairs / dt
+    sample = f"{CPU_SAMPLE_Q} query segs ({n_img} query images) x {NR_PER_GPU} ref segs x {DM}-D per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "segments matched/sec (query-seg x ref-seg pairs/s)", "value": val,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 10k query segs x 100k ref segs x 1536-D (bounded CPU sample)",
+                   "sample": sample, "k_search": K_SEARCH, "k_vote": K_VOTE},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_quick():
+    """~10-30 s of CPU work on the box's host cores: oracle port on the bounded sample (1 timed pass)."""
+    from oracle import segvlad_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    q, r = make_workload(0, "cpu")
+    qs, rn = q[:CPU_SAMPLE_Q].numpy(), r.numpy()
+    n_img = CPU_SAMPLE_Q // SEGS_PER_IMG
+    seg_range = [np.arange(i * SEGS_PER_IMG, (i + 1) * SEGS_PER_IMG) for i in range(n_img)]
+    im_inds_ref = (np.arange(NR_PER_GPU) // SEGS_PER_IMG).astype(np.int64)
+    O.flat_l2_search_fast(qs[:200], rn, K_SEARCH)      # warm BLAS threads
+    t0 = time.perf_counter()
+    D2, I = O.flat_l2_search_fast(qs, rn, K_SEARCH)
+    t1 = time.perf_counter()
+    sims, matches = O.sims_from_d2(D2, I, K_VOTE)
+    O.get_matches_wt_borda(matches, n_img, sims, seg_range, im_inds_ref, n=N_PRED)
+    t2 = time.perf_counter()
+    return {"value": CPU_SAMPLE_Q * NR_PER_GPU / (t2 - t0), "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{CPU_SAMPLE_Q} query segs x {NR_PER_GPU} ref segs x {DM}-D, 1 pass "
+                      f"(search {t1 - t0:.2f} s + vote {t2 - t1:.2f} s)"}
+
+
+def aggregation_side_bench(device, peaks):
+    """Secondary: aggregation kernel throughput on the config-2 aggregation shape (64 centres x 1536, N=1530,
+    S=128 SuperSegments/img, order-3-like density), HBM roofline from the algorithmic bytes of SURVEY 8d."""
+    from revisit_anything_b200 import _lib, engine, synth
+    lib = _lib.lib()
+    B, N, D, K, S = 16, 1530, 1536, 64, 128
+    g = torch.Generator(device=device).manual_seed(11)
+    centers = synth.make_centers(K, D, 5).to(device)
+    tok = torch.randn(B, D, N, generator=g, device=device)
+    tok = tok / tok.norm(dim=1, keepdim=True) + 0.3 * (centers / centers.norm(dim=1, keepdim=True))[
+        torch.randint(0, K, (B, N), generator=g, device=device)].permute(0, 2, 1)
+    member = torch.rand(B * S, N, generator=g, device=device) < 0.5        # SuperSegment density ~0.5 (Appendix B)
+    bits = engine.pack_membership(member)
+    counts = [S] * B
+    out = None
+    for _ in range(2):
+        out = engine.aggregate_batch(tok, N, D, 0, centers, bits, counts, None, out_dtype=torch.float64)
+    torch.cuda.synchronize()
+    lib.segvlad_profile_reset()
+    lib.segvlad_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        out = engine.aggregate_batch(tok, N, D, 0, centers, bits, counts, None, out_dtype=torch.float64)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tot, n = C.c_double(0), C.c_int(0)
+    lib.segvlad_profile_read(2, C.byref(tot), C.byref(n))
+    lib.segvlad_profile_enable(0)
+    lib.segvlad_profile_reset()
+    kern_ms = tot.value / max(n.value, 1)
+    bytes_img = N * D * 4 + K * D * 4 + S * ((N + 7) // 8) + S * K * D * 8
+    return {"workload": f"{B} images x {S} SuperSegments, N={N}, D_t={D}, K={K}, fp64 out, density 0.5",
+            "superseg_per_s": B * S / (ms * 1e-3), "ms_per_batch": ms, "kernel_ms": kern_ms,
+            "algorithmic_bytes_per_image": bytes_img,
+            "roofline": {"bound": "hbm", "achieved": B * bytes_img / (kern_ms * 1e-3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": B * bytes_img / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aggregation", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from revisit_anything_b200 import _lib, distributed as D, engine
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.lib()
+    peaks, peak_src = _peaks()
+
+    q_dev, r_dev = make_workload(rank, device)
+    n_qimg = NQ // SEGS_PER_IMG
+    qimg_off = torch.arange(0, NQ + 1, SEGS_PER_IMG, dtype=torch.int32, device=device)
+    n_rimg = world * NR_PER_GPU // SEGS_PER_IMG
+    rimg = (torch.arange(world * NR_PER_GPU, device=device) // SEGS_PER_IMG).to(torch.int32)
+    row_offset = rank * NR_PER_GPU
+    ops = D.EngineOps()
+
+    def step_resident():
+        rb = engine.Bank.prepare(r_dev)
+        qb = engine.Bank.prepare(q_dev)
+        return D.sharded_search_and_vote(ops, qb, rb, row_offset, qimg_off, rimg, n_rimg, K_SEARCH, K_VOTE, N_PRED)
+
+    q_host, r_host = q_dev.cpu().pin_memory(), r_dev.cpu().pin_memory()
+    q_stage, r_stage = torch.empty_like(q_dev), torch.empty_like(r_dev)
+    preds_host = torch.empty((n_qimg, N_PRED), dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        q_stage.copy_(q_host, non_blocking=True)
+        r_stage.copy_(r_host, non_blocking=True)
+        rb = engine.Bank.prepare(r_stage)
+        qb = engine.Bank.prepare(q_stage)
+        _, _, preds = D.sharded_search_and_vote(ops, qb, rb, row_offset, qimg_off, rimg, n_rimg, K_SEARCH, K_VOTE, N_PRED)
+        preds_host.copy_(preds, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    lib.segvlad_profile_reset()
+    lib.segvlad_profile_enable(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.segvlad_launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = lib.segvlad_launch_count() - l0
+    clocks = sampler.stop()
+    tot, n = C.c_double(0), C.c_int(0)
+    lib.segvlad_profile_read(1, C.byref(tot), C.byref(n))
+    tc_ms, tc_launches = tot.value, n.value
+    lib.segvlad_profile_read(3, C.byref(tot), C.byref(n))
+    rescore_ms = tot.value
+    lib.segvlad_profile_enable(0)
+    lib.segvlad_profile_reset()
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    pairs_step = NQ * NR_PER_GPU * world
+    ms_step = ms_total / args.steps
+    value = pairs_step / (ms_step * 1e-3)
+    e2e_val = pairs_step / (ms_e2e / args.steps * 1e-3)
+    # roofline of the dominant kernel (tcgen05 all-pairs + filter): algorithmic FLOPs = 2*D per pair
+    flops_step_rank = 2.0 * DM * NQ * NR_PER_GPU
+    tc_ms_step = tc_ms / args.steps
+    achieved = flops_step_rank / (tc_ms_step * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    out = {
+        "metric": "segments matched/sec (query-seg x ref-seg pairs/s)", "value": value, "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2-split (fp32-equivalent), fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 10k query segs x 100k ref segs x 1536-D per GPU, k_search=200, k_vote=50, "
+                               "100 query images x 100 segs; weak scaling: one 100k-row bank shard per rank",
+                   "l2": "inputs larger than L2 (fp32 bank 614 MB + bf16 planes 614 MB per rank, re-read every step)",
+                   "parallelism": f"row-sharded bank x{world}, one all-gather of per-shard top-k" if world > 1 else "single GPU",
+                   "peaks": peak_src},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(q_host.numel() * 4 + r_host.numel() * 4),
+                "d2h_bytes_per_step": int(preds_host.numel() * 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "knn_tc_filter_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "note": "algorithmic 2*D FLOP/pair; the kernel issues 3 bf16 MMA passes (hi.hi+hi.mid+mid.hi), "
+                             "so tensor-pipe utilisation is 3x this fraction; peak = sustained cuBLAS bf16",
+                     "kernel_ms_per_step": tc_ms_step, "launches_per_step": tc_launches / args.steps,
+                     "share_of_step": tc_ms_step / ms_step, "rescore_ms_per_step": rescore_ms / args.steps},
+    }
+    if rank == 0 and world == 1:
+        if not args.no_aggregation:
+            out["aggregation"] = aggregation_side_bench(device, peaks)
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_quick()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,16 @@ extern "C" {
 
 int segvlad_version(void);
 const char* segvlad_last_error(void);
+/* cumulative number of CUDA kernels this library has launched in the process (bench.py's gpu_launches) */
+uint64_t segvlad_launch_count(void);
+/* Optional kernel timing for measurement (bench.py roofline): when enabled, the dominant kernels are bracketed
+ * by CUDA events on their launch stream.  Tags: */
+#define SEGVLAD_PROF_KNN_FILTER 1 /* tcgen05 (or SIMT) all-pairs + filter kernel */
+#define SEGVLAD_PROF_AGGREGATE 2  /* masked residual aggregation kernel          */
+#define SEGVLAD_PROF_KNN_RESCORE 3
+void segvlad_profile_enable(int on);
+int segvlad_profile_read(int tag, double* total_ms, int* launches); /* synchronises the recorded events */
+void segvlad_profile_reset(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Aggregation: per-(Super)Segment masked hard-assignment VLAD.

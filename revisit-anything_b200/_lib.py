@@ -15,6 +15,10 @@ _p = C.c_void_p
 _SIGS = {
     "segvlad_version": (C.c_int, []),
     "segvlad_last_error": (C.c_char_p, []),
+    "segvlad_launch_count": (C.c_uint64, []),
+    "segvlad_profile_enable": (None, [C.c_int]),
+    "segvlad_profile_read": (C.c_int, [C.c_int, _p, _p]),
+    "segvlad_profile_reset": (None, []),
     "segvlad_aggregate_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "segvlad_aggregate_batch": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p, _p, _p,
                                           C.c_int, _p, _p, C.c_size_t, _p]),

@@ -560,14 +560,17 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   nonempty_kernel<<<S_total, 32, 0, st>>>(sup, labels, L.seg_off, B, N, W, L.cpred);
   SV_CHECK_LAUNCH();
   const int threads = (int)align_up((size_t)(D / 4), 32);
+  const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   if (out_dtype == SEGVLAD_OUT_F64) {
     aggregate_kernel<double><<<dim3(ng, K), threads, 0, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
                                                               L.grp_nseg, L.cpred, N, D, K, (double*)out, L.norms);
+    prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
   } else {
     aggregate_kernel<float><<<dim3(ng, K), threads, 0, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
                                                              L.grp_nseg, L.cpred, N, D, K, (float*)out, L.norms);
+    prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<float><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (float*)out);
   }

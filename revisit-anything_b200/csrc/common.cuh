@@ -10,6 +10,9 @@
 namespace segvlad {
 
 void set_error(const char* fmt, ...);
+void count_launch();
+int prof_begin(int tag, cudaStream_t st);  // no-ops unless segvlad_profile_enable(1)
+void prof_end(int slot, cudaStream_t st);  // every kernel launch of the library is counted (segvlad_launch_count)
 
 #define SV_CHECK_CUDA(expr)                                                                   \
   do {                                                                                        \
@@ -29,7 +32,11 @@ void set_error(const char* fmt, ...);
     }                                      \
   } while (0)
 
-#define SV_CHECK_LAUNCH() SV_CHECK_CUDA(cudaGetLastError())
+#define SV_CHECK_LAUNCH()            \
+  do {                               \
+    ::segvlad::count_launch();       \
+    SV_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -27,6 +27,7 @@ namespace segvlad {
 
 constexpr int kCandCap = 4096;     // candidate slots per query row
 constexpr int kMaxK = 1024;
+constexpr int kRescoreMargin = 32;  // extra candidates kept by the tensor-core selection before exact re-scoring
 constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
 constexpr int kStages = 2;
@@ -60,7 +61,7 @@ __device__ __forceinline__ void cand_append(const SelState& s, int row, int col,
 // ------------------------------------------------------------------------------------------------
 // bank preparation: one warp per row
 struct BankView {
-  const __nv_bfloat16* hi; const __nv_bfloat16* mid; const float* norms; int Dp;
+  const __nv_bfloat16* hi; const __nv_bfloat16* mid; const float* norms; const float* x32; int Dp;
 };
 static inline int padded_dim(int D) { return (int)align_up((size_t)D, kTileK); }
 static BankView bank_view(const void* bank, int n, int D) {
@@ -70,12 +71,13 @@ static BankView bank_view(const void* bank, int n, int D) {
   v.hi = c.take<__nv_bfloat16>((size_t)n * v.Dp);
   v.mid = c.take<__nv_bfloat16>((size_t)n * v.Dp);
   v.norms = c.take<float>(n);
+  v.x32 = c.take<float>((size_t)n * D);  // fp32 rows: exact re-scoring of the selected candidates
   return v;
 }
 
 __global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, int Dp,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                    float* __restrict__ norms) {
+                                    float* __restrict__ norms, float* __restrict__ x32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -87,6 +89,7 @@ __global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, i
     __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
     hi[(size_t)row * Dp + d] = h;
     mid[(size_t)row * Dp + d] = m;
+    if (d < D) x32[(size_t)row * D + d] = v;
     ss = fmaf(v, v, ss);
   }
   ss = warp_sum(ss);
@@ -95,7 +98,7 @@ __global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, i
 
 __global__ void bank_prepare_f64_kernel(const double* __restrict__ x, int n, int D, int Dp, int normalize_rows,
                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                        float* __restrict__ norms) {
+                                        float* __restrict__ norms, float* __restrict__ x32) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -113,6 +116,7 @@ __global__ void bank_prepare_f64_kernel(const double* __restrict__ x, int n, int
     __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
     hi[(size_t)row * Dp + d] = h;
     mid[(size_t)row * Dp + d] = m;
+    if (d < D) x32[(size_t)row * D + d] = v;
     ss = fmaf(v, v, ss);
   }
   ss = warp_sum(ss);
@@ -449,6 +453,41 @@ knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int
   }
 }
 
+// Exact re-scoring of the selected candidates: the tensor-core inner products carry the accumulation
+// error of the fp32 TMEM accumulator chain (measured ~1e-5 abs on d2 at D=1536, growing with D), which is
+// enough to order near-ties differently from an fp32 evaluation.  The <= k+margin survivors of each row are
+// re-evaluated with plain fp32 FMAs on the resident fp32 rows (one warp per candidate, lanes stride the
+// channels in float4, shuffle-tree reduction), then the final sort uses these values.
+__global__ void __launch_bounds__(256)
+knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __restrict__ r32,
+                   const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int D) {
+  const int row = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int n = sel.cnt[row];
+  if (n > kCandCap) n = kCandCap;
+  const float* qr = q32 + (size_t)(q_row0 + row) * D;
+  const float qnr = qn[q_row0 + row];
+  float* cd = sel.cand_d2 + (size_t)row * kCandCap;
+  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  const bool vec = (D & 3) == 0;
+  for (int j = w; j < n; j += 8) {
+    const int col = ci[j];
+    const float* rr = r32 + (size_t)col * D;
+    float acc = 0.f;
+    if (vec) {
+      const float4* q4 = reinterpret_cast<const float4*>(qr);
+      const float4* r4 = reinterpret_cast<const float4*>(rr);
+      for (int d = lane; d < (D >> 2); d += 32) {
+        const float4 a = __ldg(q4 + d), b = __ldg(r4 + d);
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      }
+    } else {
+      for (int d = lane; d < D; d += 32) acc = fmaf(__ldg(qr + d), __ldg(rr + d), acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) cd[j] = make_d2(qnr, rn[col], acc);
+  }
+}
+
 // k-way merge of G per-shard lists: [G][Nq][k] -> [Nq][k]
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(const float* __restrict__ d2p, const long long* __restrict__ idxp, int G, int Nq, int k,
@@ -562,14 +601,17 @@ struct SimtArgs { const float* q; const float* r; };
 static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLayout& L, int q_row0, int rows, int Nr,
                      int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
                      cudaStream_t st) {
+  // tensor-core path: select k + margin by the approximate distances, re-score those exactly, keep k
+  const int ksel = tc ? (k + kRescoreMargin) : k;
   int seen = 0;
-  const int first = next_chunk(0, k, Nr, safe);
+  const int first = next_chunk(0, ksel, Nr, safe);
   sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, first);
   SV_CHECK_LAUNCH();
   while (seen < Nr) {
-    const int chunk = next_chunk(seen, k, Nr, safe);
+    const int chunk = next_chunk(seen, ksel, Nr, safe);
     const int c0 = seen, c1 = seen + chunk;
     const int first_round = seen == 0;
+    const int pslot = prof_begin(SEGVLAD_PROF_KNN_FILTER, st);
     if (tc) {
       const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
       const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
@@ -582,10 +624,20 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLay
       knn_simt_filter_kernel<<<grid, 256, 0, st>>>(sa->q + (size_t)q_row0 * D, sa->r, L.qn + q_row0, L.rn, rows, D, c0,
                                                    c1, first_round, L.sel);
     }
+    prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     seen = c1;
     const int final_pass = seen >= Nr;
-    knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, k, final_pass, row_offset, q_row0, d2_out, idx_out);
+    if (final_pass && tc) {
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, ksel, 0, row_offset, q_row0, d2_out, idx_out);
+      SV_CHECK_LAUNCH();
+      const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
+      knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D);
+      prof_end(rslot, st);
+      SV_CHECK_LAUNCH();
+    }
+    knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, final_pass ? k : ksel, final_pass, row_offset, q_row0, d2_out,
+                                            idx_out);
     SV_CHECK_LAUNCH();
   }
   return SEGVLAD_OK;
@@ -606,6 +658,7 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
     for (int b = 0; b < n_blocks; ++b) {
       const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
       sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, 0);
+      SV_CHECK_LAUNCH();
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, k, 1, row_offset, q0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
     }
@@ -613,6 +666,7 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
   }
   if (!tc) {
     row_norms_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(sa->q, Nq, D, L.qn);
+    SV_CHECK_LAUNCH();
     row_norms_kernel<<<(Nr + 7) / 8, 256, 0, st>>>(sa->r, Nr, D, L.rn);
     SV_CHECK_LAUNCH();
   }
@@ -650,6 +704,7 @@ extern "C" size_t segvlad_bank_bytes(int n, int D) {
   c.take<__nv_bfloat16>((size_t)n * Dp);
   c.take<__nv_bfloat16>((size_t)n * Dp);
   c.take<float>(n);
+  c.take<float>((size_t)n * D);
   return c.total() + 256;
 }
 
@@ -660,7 +715,8 @@ extern "C" int segvlad_bank_prepare(const float* x, int n, int D, void* bank, vo
   if (n == 0) return SEGVLAD_OK;
   BankView v = bank_view(bank, n, D);
   bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, v.Dp, const_cast<__nv_bfloat16*>(v.hi),
-                                                   const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms));
+                                                   const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms),
+                                                   const_cast<float*>(v.x32));
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }
@@ -672,7 +728,8 @@ extern "C" int segvlad_bank_prepare_f64(const double* x, int n, int D, int norma
   if (n == 0) return SEGVLAD_OK;
   BankView v = bank_view(bank, n, D);
   bank_prepare_f64_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, v.Dp, normalize_rows, const_cast<__nv_bfloat16*>(v.hi),
-                                                       const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms));
+                                                       const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms),
+                                                       const_cast<float*>(v.x32));
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }

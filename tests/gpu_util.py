@@ -17,3 +17,13 @@ def assert_knn_close(d2, idx, d2_ref64, idx_ref64, tol=2e-6, k_check=None):
     bad = clear & (np.asarray(idx)[:, :k] != idx_ref64[:, :k])
     assert not bad.any(), f"{int(bad.sum())} index mismatches outside near-ties, first at {np.argwhere(bad)[:5]}"
     return float(clear.mean())
+
+
+def assert_desc_close(got, want, rtol=1e-5):
+    """VLAD descriptor parity: elementwise 1e-5 relative, with an absolute floor of 1e-6 x the row's largest
+    element for entries that are ~0 by cancellation."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    floor = 1e-6 * np.abs(want).max(axis=-1, keepdims=True)
+    err = np.abs(got - want)
+    bad = err > rtol * np.abs(want) + floor
+    assert not bad.any(), f"{int(bad.sum())} elements out of tolerance, max abs err {err.max():.3e}"

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+from gpu_util import assert_desc_close
 from oracle import segvlad_oracle as O
 from revisit_anything_b200 import place_rec_main, synth
 
@@ -41,12 +42,20 @@ def test_full_pipeline_tokens_to_recall():
     centers = synth.make_centers(K, D, 9)
     g = torch.Generator().manual_seed(0)
     toks_r, toks_q, masks_r, masks_q = [], [], [], []
+    def margin_ok(t):
+        return float(O.assign_labels(O.normalize_tokens(t.reshape(D, -1)), centers)[1].min()) > 1e-4
     for i in range(12):
-        t = synth.make_tokens(D, dh, dw, 500 + i, centers)
+        seed = 500 + i
+        while True:          # assignment near-ties are not reproducible in fp32 (reference included): avoid them
+            t = synth.make_tokens(D, dh, dw, seed, centers)
+            tq = t + 0.02 * torch.randn(t.shape, generator=g)
+            if margin_ok(t) and margin_ok(tq):
+                break
+            seed += 1000
         m = synth.make_masks(10 + i % 4, H // 2, W // 2, 600 + i)
         toks_r.append(t)
         masks_r.append(m)
-        toks_q.append(t + 0.02 * torch.randn(t.shape, generator=g))
+        toks_q.append(tq)
         masks_q.append(synth.jitter_masks(m, 700 + i, px=2))
     ref, im_r = place_rec_main.build_segment_descriptors(toks_r, masks_r, centers, cfg, order, desc_dim=D, batch_images=5)
     qry, im_q = place_rec_main.build_segment_descriptors(toks_q, masks_q, centers, cfg, order, desc_dim=D, batch_images=12)
@@ -56,12 +65,11 @@ def test_full_pipeline_tokens_to_recall():
         for t, m in zip(toks, masks):
             adj = torch.from_numpy(O.neighbour_adjacency(m, order))
             v, _, margin, _ = O.seg_vlad_single_img(t, m, centers, cfg, adj)
-            assert float(margin.min()) > 1e-5
             out.append(v)
         return torch.cat(out)
     ref_o, qry_o = oracle_desc(toks_r, masks_r), oracle_desc(toks_q, masks_q)
-    np.testing.assert_allclose(ref.cpu().numpy(), ref_o.numpy(), rtol=1e-5, atol=1e-9)
-    np.testing.assert_allclose(qry.cpu().numpy(), qry_o.numpy(), rtol=1e-5, atol=1e-9)
+    assert_desc_close(ref.cpu().numpy(), ref_o.numpy())
+    assert_desc_close(qry.cpu().numpy(), qry_o.numpy())
     seg_range = [np.where(im_q == i)[0] for i in range(12)]
     gt = [[i] for i in range(12)]
     k = min(200, ref.shape[0])
