@@ -32,6 +32,7 @@ constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
 constexpr int kStages = 2;
 constexpr uint32_t kStageBytes = (kTileM + kTileN) * kTileK * 2 * 2;  // hi+mid planes of Q and R tiles
+constexpr size_t kTcSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + (kTileN / 32) * 128 * 4;
 constexpr int kTcThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
 
 struct SelState {
@@ -277,6 +278,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
   // stage layout: [Qhi 16K][Qmid 16K][Rhi 32K][Rmid 32K]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* s_masks = reinterpret_cast<uint32_t*>(bars + 32);   // [kTileN/32][128] survivor bitmasks (epilogue)
   const uint32_t bar_full = smem_u32(bars + 0);        // [kStages]
   const uint32_t bar_empty = smem_u32(bars + 2);       // [kStages]
   const uint32_t bar_tfull = smem_u32(bars + 4);       // [2] accumulator ready
@@ -365,21 +367,64 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
       mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN;
+      if (first_round) {
+        // round 0: tau = +inf, every score is a candidate -> dense store at (col - c0), no counters
 #pragma unroll 1
-      for (int c = 0; c < kTileN; c += 32) {
-        uint32_t v[32];
-        tc_ld32(taddr + c, v);
-        if (row_ok) {
+        for (int c = 0; c < kTileN; c += 32) {
+          uint32_t v[32];
+          tc_ld32(taddr + c, v);
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = colbase + c + j;
+              if (col < c1) {
+                sel.cand_d2[(size_t)row * kCandCap + (col - c0)] = make_d2(qnr, __ldg(rn + col), __uint_as_float(v[j]));
+                sel.cand_idx[(size_t)row * kCandCap + (col - c0)] = col;
+              }
+            }
+          }
+        }
+      } else {
+        // pass 1: survivor bitmasks (no memory traffic); pass 2: ONE atomic slot claim per (row, tile), then
+        // re-read the accumulator chunks that hold survivors and store them.  (A per-survivor atomicAdd
+        // serialises ~700-cycle L2 round trips inside the warp and starves the MMA pipe: r1 ncu capture.)
+        uint32_t* masks = s_masks + (threadIdx.x - 64);    // [cc * 128 + epilogue thread]
+        int nsurv = 0;
+#pragma unroll 1
+        for (int cc = 0; cc < kTileN / 32; ++cc) {
+          uint32_t v[32];
+          tc_ld32(taddr + cc * 32, v);
+          uint32_t m = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int col = colbase + c + j;
-            if (col < c1) {
-              const float d2 = make_d2(qnr, __ldg(rn + col), __uint_as_float(v[j]));
-              if (first_round) {
-                sel.cand_d2[(size_t)row * kCandCap + (col - c0)] = d2;
-                sel.cand_idx[(size_t)row * kCandCap + (col - c0)] = col;
-              } else if (d2 <= tau) {
-                cand_append(sel, row, col, d2);
+            const int col = colbase + cc * 32 + j;
+            const float d2 = make_d2(qnr, __ldg(rn + min(col, c1 - 1)), __uint_as_float(v[j]));
+            if (col < c1 && d2 <= tau) m |= 1u << j;
+          }
+          m = row_ok ? m : 0u;
+          masks[cc * 128] = m;
+          nsurv += __popc(m);
+        }
+        int pos = 0;
+        if (nsurv) {
+          pos = atomicAdd(sel.cnt + row, nsurv);
+          if (pos + nsurv > kCandCap) *sel.overflow = 1;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < kTileN / 32; ++cc) {
+          const uint32_t m = masks[cc * 128];
+          if (__any_sync(0xffffffffu, m != 0u)) {   // tcgen05.ld is warp-collective
+            uint32_t v[32];
+            tc_ld32(taddr + cc * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if ((m >> j) & 1u) {
+                const int col = colbase + cc * 32 + j;
+                if (pos < kCandCap) {
+                  sel.cand_d2[(size_t)row * kCandCap + pos] = make_d2(qnr, __ldg(rn + col), __uint_as_float(v[j]));
+                  sel.cand_idx[(size_t)row * kCandCap + pos] = col;
+                }
+                ++pos;
               }
             }
           }
@@ -399,56 +444,122 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-row candidate refinement (one CTA per row).  key = (d2 bits << 32) | idx ; d2 >= +0 so the
-// unsigned order of the bits is the float order; ascending key == (d2 asc, idx asc).
+// Per-row candidate refinement (one CTA per row).
+// Non-final: radix-select the k-th smallest d2 (3 passes of 11/11/10 bits over the fp32 bit pattern; d2 >= +0
+// so unsigned order == float order), keep every candidate with d2 <= T (>= k of them; exact ties at T are all
+// kept), tau = T.  Final: the same selection, then a bitonic sort of the ~k survivors on the 64-bit key
+// (d2 bits << 32 | idx) => ascending (d2, idx), and the first k are written out (global row = offset + idx).
 __global__ void __launch_bounds__(256)
 knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int q_row0, float* __restrict__ d2_out,
                   long long* __restrict__ idx_out) {
-  __shared__ unsigned long long keys[kCandCap];
-  const int row = blockIdx.x, tid = threadIdx.x;
+  __shared__ __align__(16) unsigned s_v[kCandCap];   // d2 bit patterns   } re-used as 64-bit sort keys
+  __shared__ __align__(16) int s_i[kCandCap];        // candidate rows    } in the final pass
+  __shared__ int s_hist[2048];
+  __shared__ int s_warp[8];
+  __shared__ int s_bin, s_kk, s_out;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int n = sel.cnt[row];
   if (n > kCandCap) n = kCandCap;
   if (!final_pass && n <= k) return;
-  int P = 1;
-  while (P < n) P <<= 1;
-  const float* cd = sel.cand_d2 + (size_t)row * kCandCap;
-  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
-  for (int i = tid; i < P; i += 256)
-    keys[i] = i < n ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | (unsigned)ci[i]) : ~0ull;
+  float* cd = sel.cand_d2 + (size_t)row * kCandCap;
+  int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  for (int i = tid; i < n; i += 256) { s_v[i] = __float_as_uint(cd[i]); s_i[i] = ci[i]; }
+  int c = n;   // survivors after selection
+  if (n > k) {
+    unsigned prefix = 0, mask = 0;
+    int kk = k;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+      const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+      const int bits = pass == 2 ? 10 : 11;
+      for (int b = tid; b < 2048; b += 256) s_hist[b] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += 256) {
+        const unsigned v = s_v[i];
+        if ((v & mask) == prefix) atomicAdd(&s_hist[(v >> shift) & ((1u << bits) - 1u)], 1);
+      }
+      __syncthreads();
+      // block scan over 2048 bins (8 per thread) to find the bin holding the kk-th element
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { loc[b] = s_hist[tid * 8 + b]; sum += loc[b]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (lane == 31) s_warp[w] = incl;
+      __syncthreads();
+      int base = 0;
+      for (int ww = 0; ww < w; ++ww) base += s_warp[ww];
+      const int excl = base + incl - sum;
+      if (kk > excl && kk <= excl + sum) {
+        int run = excl;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (kk > run && kk <= run + loc[b]) { s_bin = tid * 8 + b; s_kk = kk - run; }
+          run += loc[b];
+        }
+      }
+      __syncthreads();
+      prefix |= (unsigned)s_bin << shift;
+      mask |= ((1u << bits) - 1u) << shift;
+      kk = s_kk;
+      __syncthreads();
+    }
+    const unsigned T = prefix;
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+      const unsigned v = s_v[i];
+      if (v <= T) {
+        const int pos = atomicAdd(&s_out, 1);
+        cd[pos] = __uint_as_float(v);
+        ci[pos] = s_i[i];
+      }
+    }
+    __syncthreads();
+    c = s_out;
+    if (tid == 0) { sel.cnt[row] = c; sel.tau[row] = __uint_as_float(T); }
+  }
+  if (!final_pass) return;
+  // final: sort the c (~k) survivors by (d2, idx)
   __syncthreads();
-  for (int kk = 2; kk <= P; kk <<= 1) {
-    for (int j = kk >> 1; j > 0; j >>= 1) {
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_v);   // s_v and s_i are contiguous: 32 KB
+  static_assert(sizeof(unsigned) * kCandCap * 2 == sizeof(unsigned long long) * kCandCap, "key aliasing");
+  int P = 1;
+  while (P < c) P <<= 1;
+  unsigned long long mykeys[kCandCap / 256];
+#pragma unroll
+  for (int t = 0; t < kCandCap / 256; ++t) {
+    const int i = tid + t * 256;
+    mykeys[t] = (i < c) ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | (unsigned)ci[i]) : ~0ull;
+  }
+  __syncthreads();   // everyone has read cd/ci (global) before the smem region is re-purposed
+#pragma unroll
+  for (int t = 0; t < kCandCap / 256; ++t) {
+    const int i = tid + t * 256;
+    if (i < P) keys[i] = mykeys[t];
+  }
+  __syncthreads();
+  for (int kk2 = 2; kk2 <= P; kk2 <<= 1) {
+    for (int j = kk2 >> 1; j > 0; j >>= 1) {
       for (int i = tid; i < P; i += 256) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = keys[i], b = keys[ixj];
-          if ((a > b) == ((i & kk) == 0)) { keys[i] = b; keys[ixj] = a; }
+          if ((a > b) == ((i & kk2) == 0)) { keys[i] = b; keys[ixj] = a; }
         }
       }
       __syncthreads();
     }
   }
-  if (!final_pass) {
-    float* wd = sel.cand_d2 + (size_t)row * kCandCap;
-    int* wi = sel.cand_idx + (size_t)row * kCandCap;
-    for (int i = tid; i < k; i += 256) {
-      wd[i] = __uint_as_float((unsigned)(keys[i] >> 32));
-      wi[i] = (int)(unsigned)keys[i];
-    }
-    if (tid == 0) {
-      sel.cnt[row] = k;
-      sel.tau[row] = __uint_as_float((unsigned)(keys[k - 1] >> 32));
-    }
-  } else {
-    const size_t o = (size_t)(q_row0 + row) * k;
-    for (int i = tid; i < k; i += 256) {
-      if (i < n) {
-        d2_out[o + i] = __uint_as_float((unsigned)(keys[i] >> 32));
-        idx_out[o + i] = row_offset + (long long)(unsigned)keys[i];
-      } else {
-        d2_out[o + i] = INFINITY;
-        idx_out[o + i] = -1;
-      }
+  const size_t o = (size_t)(q_row0 + row) * k;
+  for (int i = tid; i < k; i += 256) {
+    if (i < c) {
+      d2_out[o + i] = __uint_as_float((unsigned)(keys[i] >> 32));
+      idx_out[o + i] = row_offset + (long long)(unsigned)keys[i];
+    } else {
+      d2_out[o + i] = INFINITY;
+      idx_out[o + i] = -1;
     }
   }
 }
@@ -615,7 +726,7 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLay
     if (tc) {
       const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
       const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
-      const size_t smem = kStages * kStageBytes + 1024 + 256;
+      const size_t smem = kTcSmemBytes;
       knn_tc_filter_kernel<<<grid, kTcThreads, smem, st>>>(ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid, ta->q.norms,
                                                           ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK,
                                                           first_round, L.sel);
@@ -757,7 +868,7 @@ extern "C" int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr,
     SV_CHECK_CUDA(cudaGetDevice(&dev));
     SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
     SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       kStages * kStageBytes + 1024 + 256));
+                                       (int)kTcSmemBytes));
   }
   return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
                     workspace, workspace_bytes, st);

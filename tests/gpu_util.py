@@ -10,9 +10,11 @@ def assert_knn_close(d2, idx, d2_ref64, idx_ref64, tol=2e-6, k_check=None):
     k = d2.shape[1] if k_check is None else k_check
     ref = d2_ref64[:, :k]
     np.testing.assert_allclose(d2[:, :k], ref, rtol=1e-5, atol=tol)
-    gap_prev = np.concatenate([np.full((ref.shape[0], 1), np.inf), np.diff(ref, axis=1)], axis=1)
-    gap_next = np.concatenate([np.diff(ref, axis=1), np.full((ref.shape[0], 1), np.inf)], axis=1)
-    # the last column's "next" is unknown inside this slice: caller passes k_check < computed k for that
+    full = d2_ref64                      # gaps are taken on the longer reference list so that the k-th
+    gap_prev = np.concatenate([np.full((full.shape[0], 1), np.inf), np.diff(full, axis=1)], axis=1)[:, :k]
+    gap_next = np.concatenate([np.diff(full, axis=1), np.full((full.shape[0], 1), np.inf)], axis=1)[:, :k]
+    if full.shape[1] == k:               # entry also knows its next neighbour (callers pass k + 8 columns)
+        gap_next[:, -1] = 0.0
     clear = (gap_prev > 2 * tol) & (gap_next > 2 * tol)
     bad = clear & (np.asarray(idx)[:, :k] != idx_ref64[:, :k])
     assert not bad.any(), f"{int(bad.sum())} index mismatches outside near-ties, first at {np.argwhere(bad)[:5]}"
