@@ -20,6 +20,7 @@
 // (adversarially ordered banks) raise a flag; the host then re-runs with chunks <= C - k (cannot overflow).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -30,9 +31,6 @@ constexpr int kMaxK = 1024;
 constexpr int kRescoreMargin = 32;  // extra candidates kept by the tensor-core selection before exact re-scoring
 constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
-constexpr int kStages = 2;
-constexpr uint32_t kStageBytes = (kTileM + kTileN) * kTileK * 2 * 2;  // hi+mid planes of Q and R tiles
-constexpr size_t kTcSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + (kTileN / 32) * 128 * 4;
 constexpr int kTcThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
 
 struct SelState {
@@ -259,76 +257,143 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-// kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
-                                ((uint32_t)(kTileM >> 4) << 24);
+
 
 // ------------------------------------------------------------------------------------------------
-// Persistent tcgen05 all-pairs + filter kernel.
-// grid = min(#tiles, #SMs); tile t -> (col_tile = t / n_row_tiles, row_tile = t % n_row_tiles) so that
-// concurrently running CTAs share the same reference tile through L2 and the bank streams from HBM once.
+// Persistent tcgen05 all-pairs + filter kernel, templated on the CTA-group size.
+//   kCtas == 1 : one CTA per 128 x 256 tile (2-stage ring of 96 KB: Q 128 rows + R 256 rows, hi+mid planes)
+//   kCtas == 2 : a CTA PAIR (cluster 2x1x1, tcgen05 cta_group::2) per 256 x 256 tile; each CTA stages its own 128
+//                query rows and HALF of the reference tile (3-stage ring of 64 KB), the pair's MMA (M=256) reads
+//                both halves => L2->SM operand traffic per MMA drops by 1/3 (r1 ncu: cta_group::1 needs
+//                64 B/clk/SM at full tensor rate and stalled at ~53 % pipe utilisation)
+// grid = min(#tiles, #SMs) CTAs (pairs: even); tile t -> (col_tile = t / n_row_tiles, row_tile = t % n_row_tiles)
+// so concurrently running CTAs share a reference tile through L2 and the bank streams from HBM once.
+template <int kCtas> struct TcCfg;
+template <> struct TcCfg<1> { static constexpr int kStagesT = 2; static constexpr uint32_t kRRows = 256; };
+template <> struct TcCfg<2> { static constexpr int kStagesT = 3; static constexpr uint32_t kRRows = 128; };
+template <int kCtas> __host__ __device__ constexpr uint32_t tc_stage_bytes() { return (kTileM + TcCfg<kCtas>::kRRows) * kTileK * 2 * 2; }
+template <int kCtas> __host__ __device__ constexpr size_t tc_smem_bytes() {
+  return TcCfg<kCtas>::kStagesT * tc_stage_bytes<kCtas>() + 1024 /*align*/ + 256 /*barriers*/ + (kTileN / 32) * 128 * 4;
+}
+
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (-> even CTA)
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerMask), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrive on the same barrier offset in both CTAs
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the even CTA's barrier
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int kCtas>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qmid,
                      const __grid_constant__ CUtensorMap map_rhi, const __grid_constant__ CUtensorMap map_rmid,
                      const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int rows, int c0, int c1,
                      int num_kb, int first_round, SelState sel) {
+  constexpr int kSt = TcCfg<kCtas>::kStagesT;
+  constexpr uint32_t kStageB = tc_stage_bytes<kCtas>();
+  constexpr uint32_t kRPlane = TcCfg<kCtas>::kRRows * kTileK * 2;   // bytes of one R plane tile in a stage
+  constexpr int kPairM = kTileM * kCtas;                            // query rows per (pair) tile
+  // kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
+  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                              ((uint32_t)(kPairM >> 4) << 24);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B tiles
+  // 1024-byte alignment for SWIZZLE_128B tiles.  stage layout: [Qhi 16K][Qmid 16K][Rhi][Rmid]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // stage layout: [Qhi 16K][Qmid 16K][Rhi 32K][Rmid 32K]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSt * kStageB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   uint32_t* s_masks = reinterpret_cast<uint32_t*>(bars + 32);   // [kTileN/32][128] survivor bitmasks (epilogue)
-  const uint32_t bar_full = smem_u32(bars + 0);        // [kStages]
-  const uint32_t bar_empty = smem_u32(bars + 2);       // [kStages]
-  const uint32_t bar_tfull = smem_u32(bars + 4);       // [2] accumulator ready
-  const uint32_t bar_tempty = smem_u32(bars + 6);      // [2] accumulator drained
+  const uint32_t bar_full = smem_u32(bars + 0);        // [kSt]  (pairs: only the leader's copies are used)
+  const uint32_t bar_empty = smem_u32(bars + 4);       // [kSt]
+  const uint32_t bar_tfull = smem_u32(bars + 8);       // [2] accumulator ready
+  const uint32_t bar_tempty = smem_u32(bars + 10);     // [2] accumulator drained (pairs: leader's copies)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_row_tiles = (rows + kTileM - 1) / kTileM;
+  uint32_t cta_rank = 0;
+  if (kCtas == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int n_row_tiles = (rows + kPairM - 1) / kPairM;
   const int n_col_tiles = (c1 - c0 + kTileN - 1) / kTileN;
   const int n_tiles = n_row_tiles * n_col_tiles;
+  const int worker = blockIdx.x / kCtas, n_workers = gridDim.x / kCtas;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < kSt; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4 * kCtas); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: all 512 columns = two 128x256 fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  if (warp == 1) {  // TMEM: all 512 columns = two 128x256 fp32 accumulators (per CTA)
+    if (kCtas == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (one thread per CTA) =====
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rhi) : "memory");
       uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = worker; t < n_tiles; t += n_workers) {
         const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
-        const int qy = q_row0 + rt * kTileM, ry = c0 + ct * kTileN;
+        const int qy = q_row0 + rt * kPairM + (int)cta_rank * kTileM;
+        const int ry = c0 + ct * kTileN + (int)cta_rank * (int)TcCfg<kCtas>::kRRows * (kCtas - 1);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
-          mbar_arrive_expect_tx(bar_full + 8 * stage, kStageBytes);
-          tma_load_2d(sbase, &map_qhi, bar_full + 8 * stage, kb * kTileK, qy);
-          tma_load_2d(sbase + 16384, &map_qmid, bar_full + 8 * stage, kb * kTileK, qy);
-          tma_load_2d(sbase + 32768, &map_rhi, bar_full + 8 * stage, kb * kTileK, ry);
-          tma_load_2d(sbase + 65536, &map_rmid, bar_full + 8 * stage, kb * kTileK, ry);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          const uint32_t sbase = smem_u32(smem + stage * kStageB);
+          const uint32_t fb = bar_full + 8 * stage;
+          if (kCtas == 1) {
+            mbar_arrive_expect_tx(fb, kStageB);
+            tma_load_2d(sbase, &map_qhi, fb, kb * kTileK, qy);
+            tma_load_2d(sbase + 16384, &map_qmid, fb, kb * kTileK, qy);
+            tma_load_2d(sbase + 32768, &map_rhi, fb, kb * kTileK, ry);
+            tma_load_2d(sbase + 32768 + kRPlane, &map_rmid, fb, kb * kTileK, ry);
+          } else {
+            if (leader) mbar_arrive_expect_tx(fb, 2 * kStageB);   // both CTAs' bytes land on the leader's barrier
+            tma_load_2d_pair(sbase, &map_qhi, fb, kb * kTileK, qy);
+            tma_load_2d_pair(sbase + 16384, &map_qmid, fb, kb * kTileK, qy);
+            tma_load_2d_pair(sbase + 32768, &map_rhi, fb, kb * kTileK, ry);
+            tma_load_2d_pair(sbase + 32768 + kRPlane, &map_rmid, fb, kb * kTileK, ry);
+          }
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer (one thread; pairs: the leader CTA only) =====
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0, it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int t = worker; t < n_tiles; t += n_workers, ++it) {
         const uint32_t buf = it & 1, use = it >> 1;
         mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
         tc_fence_after();
@@ -336,30 +401,37 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sbase = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sbase = smem_u32(smem + stage * kStageB);
           const uint64_t qhi = umma_desc_sw128(sbase), qmid = umma_desc_sw128(sbase + 16384);
-          const uint64_t rhi = umma_desc_sw128(sbase + 32768), rmid = umma_desc_sw128(sbase + 65536);
+          const uint64_t rhi = umma_desc_sw128(sbase + 32768), rmid = umma_desc_sw128(sbase + 32768 + kRPlane);
 #pragma unroll
           for (int kk = 0; kk < kTileK / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 B along K inside the swizzle row
-            tc_mma_bf16(d_tmem, qhi + adv, rhi + adv, kIdescBf16, (kb | kk) != 0);
-            tc_mma_bf16(d_tmem, qhi + adv, rmid + adv, kIdescBf16, 1);
-            tc_mma_bf16(d_tmem, qmid + adv, rhi + adv, kIdescBf16, 1);
+            if (kCtas == 1) {
+              tc_mma_bf16(d_tmem, qhi + adv, rhi + adv, kIdesc, (kb | kk) != 0);
+              tc_mma_bf16(d_tmem, qhi + adv, rmid + adv, kIdesc, 1);
+              tc_mma_bf16(d_tmem, qmid + adv, rhi + adv, kIdesc, 1);
+            } else {
+              tc_mma_bf16_pair(d_tmem, qhi + adv, rhi + adv, kIdesc, (kb | kk) != 0);
+              tc_mma_bf16_pair(d_tmem, qhi + adv, rmid + adv, kIdesc, 1);
+              tc_mma_bf16_pair(d_tmem, qmid + adv, rhi + adv, kIdesc, 1);
+            }
           }
-          tc_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if (kCtas == 1) tc_commit(bar_empty + 8 * stage); else tc_commit_pair(bar_empty + 8 * stage);
+          if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_tfull + 8 * buf);      // accumulator complete
+        if (kCtas == 1) tc_commit(bar_tfull + 8 * buf); else tc_commit_pair(bar_tfull + 8 * buf);  // accumulator done
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    // ===== epilogue warps (TMEM lane quarter = warp % 4); each CTA drains its own 128 rows =====
     const int quarter = warp & 3;
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = worker; t < n_tiles; t += n_workers, ++it) {
       const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
       const uint32_t buf = it & 1, use = it >> 1;
-      const int row = rt * kTileM + quarter * 32 + lane;
+      const int row = rt * kPairM + (int)cta_rank * kTileM + quarter * 32 + lane;
       const bool row_ok = row < rows;
       const float qnr = row_ok ? qn[q_row0 + row] : 0.f;
       const float tau = row_ok ? sel.tau[row] : -1.f;
@@ -432,14 +504,15 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (lane == 0) { if (kCtas == 1) mbar_arrive(bar_tempty + 8 * buf); else mbar_arrive_leader(bar_tempty + 8 * buf); }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (kCtas == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -706,7 +779,7 @@ static int next_chunk(int seen, int k, int Nr, bool safe) {
   return (int)c;
 }
 
-struct TcArgs { BankView q, r; CUtensorMap mqhi, mqmid, mrhi, mrmid; int num_sms; };
+struct TcArgs { BankView q, r; CUtensorMap mqhi, mqmid, mrhi, mrmid; int num_sms; int ctas; };
 struct SimtArgs { const float* q; const float* r; };
 
 static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLayout& L, int q_row0, int rows, int Nr,
@@ -724,12 +797,29 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLay
     const int first_round = seen == 0;
     const int pslot = prof_begin(SEGVLAD_PROF_KNN_FILTER, st);
     if (tc) {
-      const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
-      const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
-      const size_t smem = kTcSmemBytes;
-      knn_tc_filter_kernel<<<grid, kTcThreads, smem, st>>>(ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid, ta->q.norms,
-                                                          ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK,
-                                                          first_round, L.sel);
+      if (ta->ctas == 2) {
+        const int n_tiles = ((rows + 2 * kTileM - 1) / (2 * kTileM)) * ((chunk + kTileN - 1) / kTileN);
+        int pairs = ta->num_sms / 2;
+        if (n_tiles < pairs) pairs = n_tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = tc_smem_bytes<2>();
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<2>, ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid,
+                                         ta->q.norms, ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK, first_round,
+                                         L.sel));
+      } else {
+        const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
+        const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
+        knn_tc_filter_kernel<1><<<grid, kTcThreads, tc_smem_bytes<1>(), st>>>(
+            ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid, ta->q.norms, ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK,
+            first_round, L.sel);
+      }
     } else {
       dim3 grid((chunk + 63) / 64, (rows + 63) / 64);
       knn_simt_filter_kernel<<<grid, 256, 0, st>>>(sa->q + (size_t)q_row0 * D, sa->r, L.qn + q_row0, L.rn, rows, D, c0,
@@ -862,13 +952,18 @@ extern "C" int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr,
     int rc;
     if ((rc = make_map(&ta.mqhi, ta.q.hi, Nq, ta.q.Dp, kTileM))) return rc;
     if ((rc = make_map(&ta.mqmid, ta.q.mid, Nq, ta.q.Dp, kTileM))) return rc;
-    if ((rc = make_map(&ta.mrhi, ta.r.hi, Nr, ta.r.Dp, kTileN))) return rc;
-    if ((rc = make_map(&ta.mrmid, ta.r.mid, Nr, ta.r.Dp, kTileN))) return rc;
+    const char* env = getenv("SEGVLAD_KNN_CTAS");      // 2 (default): CTA pairs / cta_group::2; 1: single-CTA tiles
+    ta.ctas = (env && env[0] == '1') ? 1 : 2;
+    const int r_box = ta.ctas == 2 ? kTileN / 2 : kTileN;
+    if ((rc = make_map(&ta.mrhi, ta.r.hi, Nr, ta.r.Dp, r_box))) return rc;
+    if ((rc = make_map(&ta.mrmid, ta.r.mid, Nr, ta.r.Dp, r_box))) return rc;
     int dev = 0;
     SV_CHECK_CUDA(cudaGetDevice(&dev));
     SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kTcSmemBytes));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes<1>()));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes<2>()));
   }
   return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
                     workspace, workspace_bytes, st);
