@@ -143,6 +143,18 @@ int segvlad_vote(const int64_t* matches, const float* sims, int ld, int sims_is_
                  double* pred_scores, double* scores_dense, int32_t* counts_dense, float* minmax_out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * NetVLAD + anti-burst aggregation (BASELINE config 5; data parallel over images, no collective).
+ * Replaces VLAD-BuFF/models/aggregators/aggregation.py:266-361 NetVLAD.forward (antiburst=True, getWeights
+ * :148-162, defaults ab_relu/ab_inv/ab_soft False).
+ *  x [B, D, N] fp32 backbone tokens (reference [B,D,H,W]); centroids [K,D]; conv_weight [K,D] (= alpha * c_hat,
+ *  aggregation.py:245-256); (ab_w, ab_b, ab_p) = ab_params (8,7,1 by default); out [B, K*D] fp32.
+ */
+size_t segvlad_netvlad_workspace_bytes(int B, int N, int D, int K);
+int segvlad_netvlad_antiburst(const float* x, int B, int N, int D, const float* centroids,
+                              const float* conv_weight, int K, float ab_w, float ab_b, float ab_p, float* out,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,9 @@
 
 namespace segvlad {
 
-constexpr int kSegGroup = 8;       // segments per aggregate CTA (register tile)
+constexpr int kSegGroup = 12;      // segments per aggregate CTA (register tile: 12 x 4 fp64 accumulators / thread)
+constexpr int kRingSlots = 32;     // residual-row ring (one slot per producer lane)
+constexpr unsigned kMetaEnd = 0xFFFFFFFFu;
 constexpr int kTokTile = 32;       // tokens per assign CTA
 constexpr int kAssignWarps = 8;
 constexpr float kEpsF = 1e-12f;
@@ -250,14 +252,14 @@ __global__ void superseg_union_kernel(const uint32_t* __restrict__ mem, const ui
 
 __global__ void group_transpose_kernel(const uint32_t* __restrict__ sup, const int* __restrict__ grp_seg0,
                                        const int* __restrict__ grp_nseg, int N, int W,
-                                       uint8_t* __restrict__ memT) {
+                                       uint16_t* __restrict__ memT) {
   const int g = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int s0 = grp_seg0[g], ns = grp_nseg[g];
   unsigned m = 0;
   for (int j = 0; j < ns; ++j) m |= ((sup[(size_t)(s0 + j) * W + (p >> 5)] >> (p & 31)) & 1u) << j;
-  memT[(size_t)g * N + p] = (uint8_t)m;
+  memT[(size_t)g * N + p] = (uint16_t)m;
 }
 
 // predicted #non-empty (segment, cluster) blocks per segment: one warp per segment
@@ -302,89 +304,195 @@ template <> struct Store4<float> {
   }
 };
 
-// grid (n_groups_total, K); block = ceil(D/4) threads rounded to a warp; thread t owns channels 4t..4t+3
-// of kSegGroup segment accumulators (fp64).  Membership words are CTA-uniform => branch-uniform adds.
-template <typename OutT>
-__global__ void __launch_bounds__(384, 1)
-aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, const int* __restrict__ cl_tok,
-                 const uint8_t* __restrict__ memT, const int* __restrict__ grp_img,
-                 const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
-                 const int* __restrict__ cpred, int N, int D, int K, OutT* __restrict__ out,
-                 double* __restrict__ norms) {
-  const int g = blockIdx.x, k = blockIdx.y;
-  const int b = grp_img[g], s0 = grp_seg0[g], ns = grp_nseg[g];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = blockDim.x >> 5;
-  const int d = 4 * t;
-  const bool act = d < D;
-  const int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
-  const int* toks = cl_tok + (size_t)b * N;
-  const uint8_t* mrow = memT + (size_t)g * N;
-  const float* Rb = R + (size_t)b * N * D + d;
+// ---- mbarrier / bulk-copy PTX (sm_90+; 1-D TMA bulk copy, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void agg_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void agg_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void agg_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();  // a bug, not a wait: do not hang the box
+  }
+}
+__device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
+// Masked residual aggregation, v2 (r1 ncu on v0: 1 CTA/SM, DRAM 10 %, latency-bound on the dependent
+// index -> membership -> row loads; fp64 adds predicated instead of branched).
+//   grid (n_groups_total, ceil(K / k_per_cta)); block = 32 (producer warp) + D/4 consumer threads.
+//   CTA = one group of <= kSegGroup segments of one image x a range of clusters.
+//   producer warp: walks the clusters' token lists 32 tokens at a time (lane = token), reads the CTA-uniform
+//     membership word, and for every token that is a member of some segment of the group claims the next ring
+//     slot and issues ONE bulk copy (cp.async.bulk, 6 KB residual row) that completes on the slot's mbarrier;
+//     a marker slot closes each cluster.  It runs up to kRingSlots rows ahead of the consumers.
+//   consumer thread t owns channels 4t..4t+3 of kSegGroup fp64 accumulators: per slot one LDS.128 and, for each
+//     member segment (warp-uniform branch), 4 DADDs.  At a cluster marker: block norms by warp shuffles +
+//     named barrier, scale, streaming stores, reset.
+template <typename OutT>
+__global__ void __launch_bounds__(416, 1)
+aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, const int* __restrict__ cl_tok,
+                 const uint16_t* __restrict__ memT, const int* __restrict__ grp_img,
+                 const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
+                 const int* __restrict__ cpred, int N, int D, int K, int k_per_cta, OutT* __restrict__ out,
+                 double* __restrict__ norms) {
+  extern __shared__ __align__(128) unsigned char agg_smem[];
+  const int g = blockIdx.x;
+  const int k0 = blockIdx.y * k_per_cta, k1 = min(K, k0 + k_per_cta);
+  const int b = grp_img[g], s0 = grp_seg0[g], ns = grp_nseg[g];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_cwarps = (blockDim.x >> 5) - 1;
+  const uint32_t row_bytes = (uint32_t)D * 4u;
+  float* ring = reinterpret_cast<float*>(agg_smem);
+  unsigned* meta = reinterpret_cast<unsigned*>(agg_smem + (size_t)kRingSlots * row_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + kRingSlots);
+  double* s_red = reinterpret_cast<double*>(bars + 2 * kRingSlots);      // [12 warps][kSegGroup]
+  double* s_scale = s_red + 12 * kSegGroup;                              // [kSegGroup]
+  const uint32_t bar_full = agg_smem_u32(bars), bar_empty = agg_smem_u32(bars + kRingSlots);
+  if (tid == 0) {
+    for (int i = 0; i < kRingSlots; ++i) { agg_mbar_init(bar_full + 8 * i, 1); agg_mbar_init(bar_empty + 8 * i, n_cwarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ================= producer warp =================
+    const int* toks = cl_tok + (size_t)b * N;
+    const uint16_t* mrow = memT + (size_t)g * N;
+    const float* Rb = R + (size_t)b * N * D;
+    unsigned seq = 0;   // ring sequence number of the next slot (warp-uniform)
+    for (int k = k0; k < k1; ++k) {
+      const int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
+      for (int i0 = beg; i0 < end; i0 += 32) {
+        const int i = i0 + lane;
+        int p = 0;
+        unsigned m = 0;
+        if (i < end) { p = toks[i]; m = mrow[p]; }
+        const unsigned act = __ballot_sync(0xffffffffu, m != 0u);
+        if (m != 0u) {
+          const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
+          const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
+          agg_mbar_wait(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
+          meta[slot] = m;
+          agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
+          agg_bulk_load(agg_smem_u32(ring) + slot * row_bytes, Rb + (size_t)p * D, row_bytes, bar_full + 8 * slot);
+        }
+        seq += __popc(act);
+      }
+      if (lane == 0) {   // end-of-cluster marker
+        const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
+        agg_mbar_wait(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
+        meta[slot] = kMetaEnd;
+        agg_mbar_arrive(bar_full + 8 * slot);
+      }
+      seq += 1;
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ================= consumer warps =================
+  const int t = tid - 32;                 // channel quad
+  const int cw = warp - 1;
+  const int d = 4 * t;
   double acc[kSegGroup][4];
 #pragma unroll
   for (int j = 0; j < kSegGroup; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-
-  constexpr int U = 4;
-  for (int i = beg; i < end; i += U) {
-    int p[U];
-    unsigned m[U];
-    float4 r[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      m[u] = 0;
-      if (i + u < end) { p[u] = toks[i + u]; m[u] = mrow[p[u]]; }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (m[u] && act) r[u] = __ldg(reinterpret_cast<const float4*>(Rb + (size_t)p[u] * D));
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (m[u] && act) {
-#pragma unroll
-        for (int j = 0; j < kSegGroup; ++j) {
-          if ((m[u] >> j) & 1u) {
-            acc[j][0] += (double)r[u].x;
-            acc[j][1] += (double)r[u].y;
-            acc[j][2] += (double)r[u].z;
-            acc[j][3] += (double)r[u].w;
-          }
-        }
+  unsigned seq = 0;
+  int k = k0;
+  while (k < k1) {
+    const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
+    agg_mbar_wait(bar_full + 8 * slot, gen & 1u);
+    const unsigned m = meta[slot];
+    if (m != kMetaEnd) {
+      const float4 r = *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d);
+      const double rx = (double)r.x, ry = (double)r.y, rz = (double)r.z, rw = (double)r.w;
+      // m is CTA-uniform.  ptxas if-converts `if (bit) {4 DADDs}` into predicated DADDs, which still occupy the
+      // half-rate fp64 pipe for non-member segments (r1 SASS / ncu).  A switch over each 4-segment nibble compiles
+      // to a jump table (BRX): only member segments issue adds.
+#define SV_ADD(J) { acc[J][0] += rx; acc[J][1] += ry; acc[J][2] += rz; acc[J][3] += rw; }
+#define SV_NIBBLE(J0, NIB)                                                                       \
+      switch (NIB) {                                                                              \
+        case 0: break;                                                                            \
+        case 1: SV_ADD(J0) break;                                                                 \
+        case 2: SV_ADD(J0 + 1) break;                                                             \
+        case 3: SV_ADD(J0) SV_ADD(J0 + 1) break;                                                  \
+        case 4: SV_ADD(J0 + 2) break;                                                             \
+        case 5: SV_ADD(J0) SV_ADD(J0 + 2) break;                                                  \
+        case 6: SV_ADD(J0 + 1) SV_ADD(J0 + 2) break;                                              \
+        case 7: SV_ADD(J0) SV_ADD(J0 + 1) SV_ADD(J0 + 2) break;                                   \
+        case 8: SV_ADD(J0 + 3) break;                                                             \
+        case 9: SV_ADD(J0) SV_ADD(J0 + 3) break;                                                  \
+        case 10: SV_ADD(J0 + 1) SV_ADD(J0 + 3) break;                                             \
+        case 11: SV_ADD(J0) SV_ADD(J0 + 1) SV_ADD(J0 + 3) break;                                  \
+        case 12: SV_ADD(J0 + 2) SV_ADD(J0 + 3) break;                                             \
+        case 13: SV_ADD(J0) SV_ADD(J0 + 2) SV_ADD(J0 + 3) break;                                  \
+        case 14: SV_ADD(J0 + 1) SV_ADD(J0 + 2) SV_ADD(J0 + 3) break;                              \
+        default: SV_ADD(J0) SV_ADD(J0 + 1) SV_ADD(J0 + 2) SV_ADD(J0 + 3) break;                   \
       }
+      static_assert(kSegGroup == 12, "three nibbles");
+      SV_NIBBLE(0, m & 15u)
+      SV_NIBBLE(4, (m >> 4) & 15u)
+      SV_NIBBLE(8, (m >> 8) & 15u)
+#undef SV_NIBBLE
+#undef SV_ADD
+      __syncwarp();
+      if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
+      ++seq;
+      continue;
     }
-  }
-
-  __shared__ double s_red[12][kSegGroup];
-  __shared__ double s_scale[kSegGroup];
+    // ---- cluster k complete: intra-norm, row scale, store ----
+    __syncwarp();
+    if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
+    ++seq;
 #pragma unroll
-  for (int j = 0; j < kSegGroup; ++j) {
-    double ss = acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1] + acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3];
-    ss = warp_sum(ss);
-    if (lane == 0) s_red[w][j] = ss;
-  }
-  __syncthreads();
-  if (t < kSegGroup) {
-    double tot = 0.0;
-    for (int ww = 0; ww < nw; ++ww) tot += s_red[ww][t];
-    double nrm = sqrt(tot);
-    double sc = 0.0;
-    if (t < ns) {
-      norms[(size_t)(s0 + t) * K + k] = nrm;
-      double rown = fmax(sqrt((double)cpred[s0 + t]), kEpsD);
-      sc = (1.0 / fmax(nrm, kEpsD)) * (1.0 / rown);
+    for (int j = 0; j < kSegGroup; ++j) {
+      double ss = acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1] + acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3];
+      ss = warp_sum(ss);
+      if (lane == 0) s_red[cw * kSegGroup + j] = ss;
     }
-    s_scale[t] = sc;
-  }
-  __syncthreads();
-  if (act) {
+    asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
+    if (t < kSegGroup) {
+      double tot = 0.0;
+      for (int ww = 0; ww < n_cwarps; ++ww) tot += s_red[ww * kSegGroup + t];
+      const double nrm = sqrt(tot);
+      double sc = 0.0;
+      if (t < ns) {
+        norms[(size_t)(s0 + t) * K + k] = nrm;
+        const double rown = fmax(sqrt((double)cpred[s0 + t]), kEpsD);
+        sc = (1.0 / fmax(nrm, kEpsD)) * (1.0 / rown);
+      }
+      s_scale[t] = sc;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
       if (j < ns) {
-        double sc = s_scale[j];
+        const double sc = s_scale[j];
         OutT* o = out + (size_t)(s0 + j) * K * D + (size_t)k * D + d;
         Store4<OutT>::st(o, acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
       }
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
     }
+    ++k;
   }
 }
 
@@ -442,7 +550,7 @@ __global__ void mask_to_membership_kernel(const uint8_t* __restrict__ masks, int
 
 // ------------------------------------------------------------------------------------------------
 struct AggLayout {
-  float* chatT; float* R; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint8_t* memT;
+  float* chatT; float* R; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT;
   int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
   size_t total;
 };
@@ -458,7 +566,7 @@ static AggLayout carve_agg(void* ws, int B, int N, int D, int K, int S_total) {
   L.cl_ptr = c.take<int>((size_t)B * (K + 1));
   L.cl_tok = c.take<int>((size_t)B * N);
   L.sup = c.take<uint32_t>((size_t)S_total * W);
-  L.memT = c.take<uint8_t>((size_t)max_groups * N);
+  L.memT = c.take<uint16_t>((size_t)max_groups * N);
   L.cpred = c.take<int>(S_total);
   L.norms = c.take<double>((size_t)S_total * K);
   L.seg_off = c.take<int>(B + 1);
@@ -486,7 +594,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
                             const int32_t* seg_offsets_host, const uint8_t* adj, void* out, int out_dtype,
                             int32_t* labels_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   SV_REQUIRE(B > 0 && N > 0 && D > 0 && K > 0, "aggregate: non-positive shape");
-  SV_REQUIRE(D % 4 == 0 && D <= 1536, "aggregate: D_t must be a multiple of 4 and <= 1536 (got %d)", D);
+  SV_REQUIRE(D % 128 == 0 ? D <= 1536 : (D % 4 == 0 && D <= 1536), "aggregate: D_t must be a multiple of 4 and <= 1536 (got %d)", D);
   SV_REQUIRE(K <= 128, "aggregate: K must be <= 128 (got %d)", K);
   const int layout = token_layout & 1, prenorm = (token_layout & SEGVLAD_TOKENS_PRENORMALIZED) ? 1 : 0;
   SV_REQUIRE((token_layout & ~3) == 0, "aggregate: bad token_layout");
@@ -559,17 +667,25 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   SV_CHECK_LAUNCH();
   nonempty_kernel<<<S_total, 32, 0, st>>>(sup, labels, L.seg_off, B, N, W, L.cpred);
   SV_CHECK_LAUNCH();
-  const int threads = (int)align_up((size_t)(D / 4), 32);
+  // one warp of producers + D/4 consumer threads; clusters are split over blockIdx.y until the grid has
+  // >= ~2 CTAs per SM (single-image calls) -- batched calls keep every cluster of a group in one CTA
+  const int threads = 32 + D / 4;
+  int k_per_cta = K;
+  while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 2 * 148) k_per_cta = (k_per_cta + 1) / 2;
+  const dim3 agrid(ng, (K + k_per_cta - 1) / k_per_cta);
+  const size_t asmem = (size_t)kRingSlots * D * 4 + kRingSlots * 4 + 2 * kRingSlots * 8 + 13 * kSegGroup * 8 + 64;
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   if (out_dtype == SEGVLAD_OUT_F64) {
-    aggregate_kernel<double><<<dim3(ng, K), threads, 0, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
-                                                              L.grp_nseg, L.cpred, N, D, K, (double*)out, L.norms);
+    SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+    aggregate_kernel<double><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
+                                                           L.grp_nseg, L.cpred, N, D, K, k_per_cta, (double*)out, L.norms);
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
   } else {
-    aggregate_kernel<float><<<dim3(ng, K), threads, 0, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
-                                                             L.grp_nseg, L.cpred, N, D, K, (float*)out, L.norms);
+    SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
+    aggregate_kernel<float><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
+                                                          L.grp_nseg, L.cpred, N, D, K, k_per_cta, (float*)out, L.norms);
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<float><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (float*)out);

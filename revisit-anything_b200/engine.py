@@ -248,3 +248,23 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
                              _ptr(pscores), _ptr(scores), _ptr(counts), _ptr(mm), _ptr(ws), ws.numel(), _stream()),
           "segvlad_vote")
     return VoteResult(preds, pscores, scores, counts, mm)
+
+
+# --------------------------------------------------------------------------------------------
+# NetVLAD + anti-burst (config 5)
+# --------------------------------------------------------------------------------------------
+def netvlad_antiburst(x: torch.Tensor, centroids: torch.Tensor, conv_weight: torch.Tensor,
+                      ab_params=(8.0, 7.0, 1.0)) -> torch.Tensor:
+    """x [B,D,N] (or [B,D,H,W]) fp32 CUDA -> [B, K*D] fp32 (aggregation.py:266-361 semantics, antiburst on)."""
+    _need_cuda(x, centroids, conv_weight)
+    B, D = x.shape[0], x.shape[1]
+    x = x.reshape(B, D, -1).contiguous().float()
+    N = x.shape[2]
+    K = centroids.shape[0]
+    cw = conv_weight.reshape(K, D).contiguous().float()
+    out = torch.empty((B, K * D), dtype=torch.float32, device=x.device)
+    ws = _ws(lib().segvlad_netvlad_workspace_bytes(B, N, D, K), x.device)
+    check(lib().segvlad_netvlad_antiburst(_ptr(x), B, N, D, _ptr(centroids.contiguous().float()), _ptr(cw), K,
+                                          float(ab_params[0]), float(ab_params[1]), float(ab_params[2]), _ptr(out),
+                                          _ptr(ws), ws.numel(), _stream()), "segvlad_netvlad_antiburst")
+    return out
