@@ -273,15 +273,13 @@ def main():
         return D.sharded_search_and_vote(ops, qb, rb, row_offset, qimg_off, rimg, n_rimg, K_SEARCH, K_VOTE, N_PRED)
 
     q_host, r_host = q_dev.cpu().pin_memory(), r_dev.cpu().pin_memory()
-    q_stage, r_stage = torch.empty_like(q_dev), torch.empty_like(r_dev)
     preds_host = torch.empty((n_qimg, N_PRED), dtype=torch.int32).pin_memory()
 
     def step_e2e():
-        q_stage.copy_(q_host, non_blocking=True)
-        r_stage.copy_(r_host, non_blocking=True)
-        rb = engine.Bank.prepare(r_stage)
-        qb = engine.Bank.prepare(q_stage)
-        _, _, preds = D.sharded_search_and_vote(ops, qb, rb, row_offset, qimg_off, rimg, n_rimg, K_SEARCH, K_VOTE, N_PRED)
+        # public host-input call: H2D of both matrices is inside the timed region (pipelined with the scan)
+        d2, idx, _, _ = engine.knn_from_host(q_host, r_host, K_SEARCH, row_offset)
+        d2, idx = D.gather_merge(ops, d2, idx)
+        preds = ops.vote(idx, d2, qimg_off, rimg, n_rimg, N_PRED, K_VOTE)
         preds_host.copy_(preds, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 

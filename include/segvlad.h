@@ -113,6 +113,14 @@ size_t segvlad_knn_workspace_bytes(int Nq, int Nr, int D, int k);
 int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D,
                 int k, float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
                 void* stream);
+/* Same search with both descriptor matrices in (pinned) HOST memory -- what the reference hands to faiss
+ * (segFtVLAD1/2 are CPU tensors, place_rec_main.py:53-61).  The fp32 rows are copied sub-chunk by sub-chunk on a copy
+ * stream straight into the banks' fp32 regions while earlier sub-chunks are split and scanned on `stream`, so the PCIe
+ * transfer overlaps the tensor-core scan.  qbank / rbank: device buffers of segvlad_bank_bytes() (outputs; the banks are
+ * resident and re-usable with segvlad_knn afterwards).  copy_stream may be NULL (library-owned stream). */
+int segvlad_knn_from_host(const float* q_host, int Nq, const float* r_host, int Nr, int64_t row_offset, int D,
+                          int k, void* qbank, void* rbank, float* d2_out, int64_t* idx_out, void* workspace,
+                          size_t workspace_bytes, void* stream, void* copy_stream);
 /* Same contract on the raw fp32 matrices with plain fp32 FFMA inner products (no tensor cores):
  * the on-device cross-check for the tcgen05 path (tests / debugging); same workspace size. */
 int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, int64_t row_offset, int D, int k,

@@ -330,6 +330,17 @@ __device__ __forceinline__ void agg_mbar_wait(uint32_t bar, uint32_t parity) {
     if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();  // a bug, not a wait: do not hang the box
   }
 }
+__device__ __forceinline__ bool agg_mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking probe
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -387,10 +398,18 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
         unsigned m = 0;
         if (i < end) { p = toks[i]; m = mrow[p]; }
         const unsigned act = __ballot_sync(0xffffffffu, m != 0u);
+        const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
+        const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
+        // converged polling: every lane probes ITS slot's empty barrier without blocking (a per-lane try_wait
+        // spin would serialise the 32 lanes' waits)
+        bool ok = (m == 0u);
+        const long long t0 = clock64();
+        for (unsigned spin = 0;; ++spin) {
+          if (!ok) ok = agg_mbar_test(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
+          if (__all_sync(0xffffffffu, ok)) break;
+          if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();
+        }
         if (m != 0u) {
-          const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
-          const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
-          agg_mbar_wait(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
           meta[slot] = m;
           agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
           agg_bulk_load(agg_smem_u32(ring) + slot * row_bytes, Rb + (size_t)p * D, row_bytes, bar_full + 8 * slot);
@@ -413,6 +432,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   const int t = tid - 32;                 // channel quad
   const int cw = warp - 1;
   const int d = 4 * t;
+  const bool act_ch = d < D;              // last warp may be partially idle when D % 128 != 0
   double acc[kSegGroup][4];
 #pragma unroll
   for (int j = 0; j < kSegGroup; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
@@ -423,7 +443,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     agg_mbar_wait(bar_full + 8 * slot, gen & 1u);
     const unsigned m = meta[slot];
     if (m != kMetaEnd) {
-      const float4 r = *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d);
+      const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
       const double rx = (double)r.x, ry = (double)r.y, rz = (double)r.z, rw = (double)r.w;
       // m is CTA-uniform.  ptxas if-converts `if (bit) {4 DADDs}` into predicated DADDs, which still occupy the
       // half-rate fp64 pipe for non-member segments (r1 SASS / ncu).  A switch over each 4-segment nibble compiles
@@ -485,7 +505,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
-      if (j < ns) {
+      if (j < ns && act_ch) {
         const double sc = s_scale[j];
         OutT* o = out + (size_t)(s0 + j) * K * D + (size_t)k * D + d;
         Store4<OutT>::st(o, acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
@@ -669,7 +689,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   SV_CHECK_LAUNCH();
   // one warp of producers + D/4 consumer threads; clusters are split over blockIdx.y until the grid has
   // >= ~2 CTAs per SM (single-image calls) -- batched calls keep every cluster of a group in one CTA
-  const int threads = 32 + D / 4;
+  const int threads = 32 + (int)align_up((size_t)(D / 4), 32);
   int k_per_cta = K;
   while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 2 * 148) k_per_cta = (k_per_cta + 1) / 2;
   const dim3 agrid(ng, (K + k_per_cta - 1) / k_per_cta);

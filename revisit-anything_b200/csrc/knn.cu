@@ -95,6 +95,28 @@ __global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, i
   if (lane == 0) norms[row] = ss;
 }
 
+// rows [row0, row0+nrows) whose fp32 values already sit in the bank's x32 region (host-streamed path)
+__global__ void bank_prepare_rows_kernel(const float* __restrict__ x32, int row0, int nrows, int D, int Dp,
+                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
+                                         float* __restrict__ norms) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= nrows) return;
+  const int row = row0 + r;
+  const float* xr = x32 + (size_t)row * D;
+  float ss = 0.f;
+  for (int d = lane; d < Dp; d += 32) {
+    float v = d < D ? xr[d] : 0.f;
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi[(size_t)row * Dp + d] = h;
+    mid[(size_t)row * Dp + d] = m;
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) norms[row] = ss;
+}
+
 __global__ void bank_prepare_f64_kernel(const double* __restrict__ x, int n, int D, int Dp, int normalize_rows,
                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
                                         float* __restrict__ norms, float* __restrict__ x32) {
@@ -446,12 +468,27 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
           uint32_t v[32];
           tc_ld32(taddr + c, v);
           if (row_ok) {
+            // 16-byte stores: a warp-wide 4-byte store at a 16 KB row stride touches 32 sectors for 128 useful bytes
+            float* cd = sel.cand_d2 + (size_t)row * kCandCap + (colbase + c - c0);
+            int* ci = sel.cand_idx + (size_t)row * kCandCap + (colbase + c - c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 32; j += 4) {
               const int col = colbase + c + j;
-              if (col < c1) {
-                sel.cand_d2[(size_t)row * kCandCap + (col - c0)] = make_d2(qnr, __ldg(rn + col), __uint_as_float(v[j]));
-                sel.cand_idx[(size_t)row * kCandCap + (col - c0)] = col;
+              if (col + 3 < c1) {
+                float4 d4;
+                d4.x = make_d2(qnr, __ldg(rn + col + 0), __uint_as_float(v[j + 0]));
+                d4.y = make_d2(qnr, __ldg(rn + col + 1), __uint_as_float(v[j + 1]));
+                d4.z = make_d2(qnr, __ldg(rn + col + 2), __uint_as_float(v[j + 2]));
+                d4.w = make_d2(qnr, __ldg(rn + col + 3), __uint_as_float(v[j + 3]));
+                *reinterpret_cast<float4*>(cd + j) = d4;
+                *reinterpret_cast<int4*>(ci + j) = make_int4(col, col + 1, col + 2, col + 3);
+              } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (col + u < c1) {
+                    cd[j + u] = make_d2(qnr, __ldg(rn + col + u), __uint_as_float(v[j + u]));
+                    ci[j + u] = col + u;
+                  }
               }
             }
           }
@@ -782,19 +819,57 @@ static int next_chunk(int seen, int k, int Nr, bool safe) {
 struct TcArgs { BankView q, r; CUtensorMap mqhi, mqmid, mrhi, mrmid; int num_sms; int ctas; };
 struct SimtArgs { const float* q; const float* r; };
 
+// Host-streamed reference bank: fp32 rows arrive from pinned host memory on a copy stream, sub-chunk by
+// sub-chunk, directly into the bank's fp32 region; the compute stream waits for each sub-chunk's event, splits it
+// into bf16 planes and scans it while the next sub-chunks are still in flight over PCIe.
+struct HostFeed {
+  const float* r_host;     // [Nr, D] pinned host rows
+  cudaStream_t copy;       // copy stream
+  int sub_rows;            // rows per copy / scan sub-chunk (multiple of kTileN)
+};
+struct SubChunk { int c0, c1; int first_round; int last_of_round; int final_pass; };
+
 static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLayout& L, int q_row0, int rows, int Nr,
                      int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
-                     cudaStream_t st) {
+                     cudaStream_t st, const HostFeed* feed = nullptr) {
   // tensor-core path: select k + margin by the approximate distances, re-score those exactly, keep k
   const int ksel = tc ? (k + kRescoreMargin) : k;
-  int seen = 0;
   const int first = next_chunk(0, ksel, Nr, safe);
   sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, first);
   SV_CHECK_LAUNCH();
-  while (seen < Nr) {
+  // schedule: rounds (refine boundaries) split into sub-chunks (one filter launch each)
+  SubChunk sched[512];
+  int ns = 0;
+  for (int seen = 0; seen < Nr;) {
     const int chunk = next_chunk(seen, ksel, Nr, safe);
-    const int c0 = seen, c1 = seen + chunk;
-    const int first_round = seen == 0;
+    const int sub = (feed && seen > 0) ? feed->sub_rows : chunk;
+    for (int s0 = seen; s0 < seen + chunk; s0 += sub) {
+      SV_REQUIRE(ns < 512, "knn: schedule too long");
+      const int s1 = (s0 + sub < seen + chunk) ? s0 + sub : seen + chunk;
+      sched[ns++] = {s0, s1, seen == 0, s1 == seen + chunk, s1 == Nr};
+    }
+    seen += chunk;
+  }
+  cudaEvent_t ev[512];
+  if (feed) {
+    for (int i = 0; i < ns; ++i) {
+      SV_CHECK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+      const size_t off = (size_t)sched[i].c0 * D, cnt = (size_t)(sched[i].c1 - sched[i].c0) * D;
+      SV_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(ta->r.x32) + off, feed->r_host + off, cnt * sizeof(float),
+                                    cudaMemcpyHostToDevice, feed->copy));
+      SV_CHECK_CUDA(cudaEventRecord(ev[i], feed->copy));
+    }
+  }
+  for (int i = 0; i < ns; ++i) {
+    const int c0 = sched[i].c0, c1 = sched[i].c1, chunk = c1 - c0, first_round = sched[i].first_round;
+    if (feed) {
+      SV_CHECK_CUDA(cudaStreamWaitEvent(st, ev[i], 0));
+      bank_prepare_rows_kernel<<<(chunk + 7) / 8, 256, 0, st>>>(ta->r.x32, c0, chunk, D, ta->r.Dp,
+                                                                const_cast<__nv_bfloat16*>(ta->r.hi),
+                                                                const_cast<__nv_bfloat16*>(ta->r.mid),
+                                                                const_cast<float*>(ta->r.norms));
+      SV_CHECK_LAUNCH();
+    }
     const int pslot = prof_begin(SEGVLAD_PROF_KNN_FILTER, st);
     if (tc) {
       if (ta->ctas == 2) {
@@ -827,8 +902,8 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLay
     }
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
-    seen = c1;
-    const int final_pass = seen >= Nr;
+    if (!sched[i].last_of_round) continue;
+    const int final_pass = sched[i].final_pass;
     if (final_pass && tc) {
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, ksel, 0, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
@@ -841,11 +916,14 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLay
                                             idx_out);
     SV_CHECK_LAUNCH();
   }
+  if (feed)
+    for (int i = 0; i < ns; ++i) cudaEventDestroy(ev[i]);
   return SEGVLAD_OK;
 }
 
 static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, int D, int k, long long row_offset,
-                      float* d2_out, long long* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                      float* d2_out, long long* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                      const HostFeed* feed = nullptr) {
   SV_REQUIRE(Nq >= 0 && Nr >= 0 && D > 0, "knn: bad shape");
   SV_REQUIRE(k > 0 && k <= kMaxK, "knn: k must be in [1, %d] (got %d)", kMaxK, k);
   if (Nq == 0) return SEGVLAD_OK;
@@ -873,7 +951,8 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
   }
   for (int b = 0; b < n_blocks; ++b) {
     const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
-    int rc = run_block(tc, ta, sa, L, q0, rows, Nr, D, k, row_offset, false, d2_out, idx_out, st);
+    int rc = run_block(tc, ta, sa, L, q0, rows, Nr, D, k, row_offset, false, d2_out, idx_out, st,
+                       b == 0 ? feed : nullptr);   // after the first query block the bank is resident
     if (rc) return rc;
     SV_CHECK_CUDA(cudaMemcpyAsync(L.flags + b, L.sel.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
   }
@@ -941,32 +1020,75 @@ extern "C" size_t segvlad_knn_workspace_bytes(int Nq, int Nr, int D, int k) {
   return carve_knn(nullptr, Nq, Nr).total;
 }
 
+static int tc_setup(TcArgs& ta, const void* qbank, int Nq, const void* rbank, int Nr, int D) {
+  ta.q = bank_view(qbank, Nq, D);
+  ta.r = bank_view(rbank, Nr, D);
+  int rc;
+  const char* env = getenv("SEGVLAD_KNN_CTAS");      // 2 (default): CTA pairs / cta_group::2; 1: single-CTA tiles
+  ta.ctas = (env && env[0] == '1') ? 1 : 2;
+  const int r_box = ta.ctas == 2 ? kTileN / 2 : kTileN;
+  if ((rc = make_map(&ta.mqhi, ta.q.hi, Nq, ta.q.Dp, kTileM))) return rc;
+  if ((rc = make_map(&ta.mqmid, ta.q.mid, Nq, ta.q.Dp, kTileM))) return rc;
+  if ((rc = make_map(&ta.mrhi, ta.r.hi, Nr, ta.r.Dp, r_box))) return rc;
+  if ((rc = make_map(&ta.mrmid, ta.r.mid, Nr, ta.r.Dp, r_box))) return rc;
+  int dev = 0;
+  SV_CHECK_CUDA(cudaGetDevice(&dev));
+  SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
+  SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc_smem_bytes<1>()));
+  SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc_smem_bytes<2>()));
+  return SEGVLAD_OK;
+}
+
 extern "C" int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D, int k,
                            float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   SV_REQUIRE(D > 0, "knn: bad D");
   TcArgs ta;
   if (Nq > 0 && Nr > 0) {
-    ta.q = bank_view(qbank, Nq, D);
-    ta.r = bank_view(rbank, Nr, D);
-    int rc;
-    if ((rc = make_map(&ta.mqhi, ta.q.hi, Nq, ta.q.Dp, kTileM))) return rc;
-    if ((rc = make_map(&ta.mqmid, ta.q.mid, Nq, ta.q.Dp, kTileM))) return rc;
-    const char* env = getenv("SEGVLAD_KNN_CTAS");      // 2 (default): CTA pairs / cta_group::2; 1: single-CTA tiles
-    ta.ctas = (env && env[0] == '1') ? 1 : 2;
-    const int r_box = ta.ctas == 2 ? kTileN / 2 : kTileN;
-    if ((rc = make_map(&ta.mrhi, ta.r.hi, Nr, ta.r.Dp, r_box))) return rc;
-    if ((rc = make_map(&ta.mrmid, ta.r.mid, Nr, ta.r.Dp, r_box))) return rc;
-    int dev = 0;
-    SV_CHECK_CUDA(cudaGetDevice(&dev));
-    SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc_smem_bytes<1>()));
-    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)tc_smem_bytes<2>()));
+    int rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
+    if (rc) return rc;
   }
   return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
                     workspace, workspace_bytes, st);
+}
+
+extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r_host, int Nr, int64_t row_offset, int D,
+                                     int k, void* qbank, void* rbank, float* d2_out, int64_t* idx_out, void* workspace,
+                                     size_t workspace_bytes, void* stream_, void* copy_stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(D > 0 && Nq > 0 && Nr > 0 && q_host && r_host && qbank && rbank, "knn_from_host: bad arguments");
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(qbank) & 255) == 0 && (reinterpret_cast<uintptr_t>(rbank) & 255) == 0,
+             "knn_from_host: banks must be 256-byte aligned");
+  static cudaStream_t own_copy = nullptr;
+  cudaStream_t cp = reinterpret_cast<cudaStream_t>(copy_stream_);
+  if (!cp) {
+    if (!own_copy) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&own_copy, cudaStreamNonBlocking));
+    cp = own_copy;
+  }
+  TcArgs ta;
+  int rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
+  if (rc) return rc;
+  // order the copy stream after everything already queued on the compute stream (buffer re-use across calls)
+  cudaEvent_t e0, eq;
+  SV_CHECK_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+  SV_CHECK_CUDA(cudaEventCreateWithFlags(&eq, cudaEventDisableTiming));
+  SV_CHECK_CUDA(cudaEventRecord(e0, st));
+  SV_CHECK_CUDA(cudaStreamWaitEvent(cp, e0, 0));
+  SV_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(ta.q.x32), q_host, sizeof(float) * (size_t)Nq * D,
+                                cudaMemcpyHostToDevice, cp));
+  SV_CHECK_CUDA(cudaEventRecord(eq, cp));
+  SV_CHECK_CUDA(cudaStreamWaitEvent(st, eq, 0));
+  bank_prepare_rows_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(ta.q.x32, 0, Nq, D, ta.q.Dp, const_cast<__nv_bfloat16*>(ta.q.hi),
+                                                        const_cast<__nv_bfloat16*>(ta.q.mid), const_cast<float*>(ta.q.norms));
+  SV_CHECK_LAUNCH();
+  HostFeed feed{r_host, cp, 16384};
+  rc = knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out), workspace,
+                  workspace_bytes, st, &feed);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(eq);
+  return rc;
 }
 
 extern "C" int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, int64_t row_offset, int D, int k,

@@ -67,9 +67,8 @@ class EngineOps:
         return res.preds
 
 
-def sharded_search(ops, qbank, local_rbank, row_offset: int, k: int, group=None):
-    """Local top-k on this rank's shard -> one all-gather -> merged global top-k (on every rank)."""
-    d2, idx = ops.search(qbank, local_rbank, k, row_offset)
+def gather_merge(ops, d2, idx, group=None):
+    """Per-shard top-k lists -> ONE all-gather -> merged global top-k (identical on every rank)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return d2, idx
@@ -79,6 +78,12 @@ def sharded_search(ops, qbank, local_rbank, row_offset: int, k: int, group=None)
     dist.all_gather_into_tensor(gathered, payload, group=group)      # the single collective of the path
     d2_parts, idx_parts = unpack_topk(gathered.view((world,) + tuple(payload.shape)))
     return ops.merge(d2_parts, idx_parts)
+
+
+def sharded_search(ops, qbank, local_rbank, row_offset: int, k: int, group=None):
+    """Local top-k on this rank's shard -> one all-gather -> merged global top-k (on every rank)."""
+    d2, idx = ops.search(qbank, local_rbank, k, row_offset)
+    return gather_merge(ops, d2, idx, group)
 
 
 def sharded_search_and_vote(ops, qbank, local_rbank, row_offset: int, qimg_offsets, rseg_to_rimg, n_rimg: int,

@@ -182,6 +182,26 @@ def knn(q: Bank, r: Bank, k: int, row_offset: int = 0) -> Tuple[torch.Tensor, to
     return d2, idx
 
 
+def knn_from_host(q_host: torch.Tensor, r_host: torch.Tensor, k: int, row_offset: int = 0, device=None):
+    """Search with both fp32 descriptor matrices in host memory (pin them for full PCIe rate): the H2D transfer
+    of the reference bank is pipelined with the tensor-core scan.  Returns (d2, idx, qbank, rbank) -- the banks are
+    resident afterwards."""
+    assert not q_host.is_cuda and not r_host.is_cuda and q_host.dtype == torch.float32 and r_host.dtype == torch.float32
+    q_host, r_host = q_host.contiguous(), r_host.contiguous()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+    Nq, D = q_host.shape
+    Nr = r_host.shape[0]
+    qb = Bank(_ws(lib().segvlad_bank_bytes(Nq, D), dev), Nq, D)
+    rb = Bank(_ws(lib().segvlad_bank_bytes(Nr, D), dev), Nr, D)
+    d2 = torch.empty((Nq, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((Nq, k), dtype=torch.int64, device=dev)
+    ws = _ws(lib().segvlad_knn_workspace_bytes(Nq, Nr, D, k), dev)
+    check(lib().segvlad_knn_from_host(C.c_void_p(q_host.data_ptr()), Nq, C.c_void_p(r_host.data_ptr()), Nr,
+                                      int(row_offset), D, k, _ptr(qb.buf), _ptr(rb.buf), _ptr(d2), _ptr(idx), _ptr(ws),
+                                      ws.numel(), _stream(), None), "segvlad_knn_from_host")
+    return d2, idx, qb, rb
+
+
 def knn_simt(q: torch.Tensor, r: torch.Tensor, k: int, row_offset: int = 0):
     """fp32 FFMA cross-check path (same selection machinery, no tensor cores)."""
     _need_cuda(q, r)

@@ -31,12 +31,18 @@ def search_and_vote(seg_ft_ref: torch.Tensor, seg_ft_qry: torch.Tensor, seg_rang
                     pca: bool, k_search: int = K_SEARCH, k_vote: int = K_VOTE, n_pred: int = N_PRED):
     """Device-resident core of recall_segloc: returns (d2 [Nq,k], idx [Nq,k], VoteResult)."""
     dev = _dev()
-    f64 = seg_ft_ref.dtype == torch.float64
-    prep = (lambda x: engine.Bank.prepare_f64(x.to(dev), normalize_rows=pca)) if f64 or pca else \
-           (lambda x: engine.Bank.prepare(x.to(dev)))
-    rbank = prep(seg_ft_ref)
-    qbank = prep(seg_ft_qry)
-    d2, idx = engine.knn(qbank, rbank, k_search)
+    host_f32 = (not seg_ft_ref.is_cuda and not seg_ft_qry.is_cuda and not pca
+                and seg_ft_ref.dtype == torch.float32 and seg_ft_qry.dtype == torch.float32)
+    if host_f32:
+        # CPU fp32 descriptors (pin them for full PCIe rate): stream the bank while scanning it
+        d2, idx, _, _ = engine.knn_from_host(seg_ft_qry, seg_ft_ref, k_search)
+    else:
+        f64 = seg_ft_ref.dtype == torch.float64
+        prep = (lambda x: engine.Bank.prepare_f64(x.to(dev), normalize_rows=pca)) if f64 or pca else \
+               (lambda x: engine.Bank.prepare(x.to(dev)))
+        rbank = prep(seg_ft_ref)
+        qbank = prep(seg_ft_qry)
+        d2, idx = engine.knn(qbank, rbank, k_search)
     perm, off = func_vpr._ranges_to_offsets(seg_range_q, n_qimg)
     m, s = idx, d2
     if perm is not None:

@@ -125,3 +125,19 @@ def test_bank_prepare_f64_normalizes_like_normalizeFeat():
     xn, yn = O.normalize_feat(x.numpy()), O.normalize_feat(y.numpy())
     d64, i64 = O.flat_l2_search_fp64(yn, xn, 58)
     assert_knn_close(d2.cpu().numpy(), idx.cpu().numpy(), d64, i64, k_check=50)
+
+
+def test_knn_from_host_streamed_matches_resident():
+    # pinned host inputs, reference bank streamed in sub-chunks while being scanned; result == resident search
+    q, r = synth.make_descriptor_bank(700, 50000, 256, seed=12, planted=100, device=DEV)
+    d2_res, idx_res = _run_tc(q, r, 200, off=77)
+    qh, rh = q.cpu().pin_memory(), r.cpu().pin_memory()
+    d2, idx, qb, rb = engine.knn_from_host(qh, rh, 200, row_offset=77)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d2.cpu().numpy(), d2_res)
+    np.testing.assert_array_equal(idx.cpu().numpy(), idx_res)
+    d2b, idxb = engine.knn(qb, rb, 200, row_offset=77)          # the banks are resident and re-usable afterwards
+    np.testing.assert_array_equal(d2b.cpu().numpy(), d2_res)
+    # pageable (non-pinned) host memory also works (no overlap, same answer)
+    d2p, idxp, _, _ = engine.knn_from_host(q.cpu(), r.cpu(), 200, row_offset=77)
+    np.testing.assert_array_equal(idxp.cpu().numpy(), idx_res)
