@@ -390,40 +390,63 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     const uint16_t* mrow = memT + (size_t)g * N;
     const float* Rb = R + (size_t)b * N * D;
     unsigned seq = 0;   // ring sequence number of the next slot (warp-uniform)
-    for (int k = k0; k < k1; ++k) {
-      const int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
-      for (int i0 = beg; i0 < end; i0 += 32) {
-        const int i = i0 + lane;
-        int p = 0;
-        unsigned m = 0;
-        if (i < end) { p = toks[i]; m = mrow[p]; }
-        const unsigned act = __ballot_sync(0xffffffffu, m != 0u);
-        const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
-        const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
-        // converged polling: every lane probes ITS slot's empty barrier without blocking (a per-lane try_wait
-        // spin would serialise the 32 lanes' waits)
-        bool ok = (m == 0u);
+    // software-pipelined window walk: the (token id -> membership word) loads of window w+1 are in flight while
+    // window w is issued; a window is issued in 4 sub-batches of 8 lanes so that slot re-use is waited for at a
+    // quarter-ring granularity (a whole-warp batch would need the entire ring drained before every batch)
+    int k = k0;
+    int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
+    int i0 = beg;
+    int p_cur = 0;
+    unsigned m_cur = 0;
+    if (i0 + lane < end) { p_cur = toks[i0 + lane]; m_cur = mrow[p_cur]; }
+    while (k < k1) {
+      const bool last_in_cluster = (i0 + 32 >= end);
+      int nk = k, ni0 = i0 + 32, nbeg = beg, nend = end;
+      if (last_in_cluster) {
+        nk = k + 1;
+        if (nk < k1) {
+          nbeg = cl_ptr[(size_t)b * (K + 1) + nk];
+          nend = cl_ptr[(size_t)b * (K + 1) + nk + 1];
+          ni0 = nbeg;
+        }
+      }
+      int p_nxt = 0;
+      unsigned m_nxt = 0;
+      if (nk < k1 && ni0 + lane < nend) { p_nxt = toks[ni0 + lane]; m_nxt = mrow[p_nxt]; }   // prefetch
+
+      const unsigned act = __ballot_sync(0xffffffffu, m_cur != 0u);
+      const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
+      const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {
+        const bool mine = (m_cur != 0u) && ((lane >> 3) == sub);
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        // converged polling: every lane probes ITS slot's empty barrier without blocking
+        bool ok = !mine;
         const long long t0 = clock64();
         for (unsigned spin = 0;; ++spin) {
           if (!ok) ok = agg_mbar_test(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
           if (__all_sync(0xffffffffu, ok)) break;
           if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();
         }
-        if (m != 0u) {
-          meta[slot] = m;
+        if (mine) {
+          meta[slot] = m_cur;
           agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
-          agg_bulk_load(agg_smem_u32(ring) + slot * row_bytes, Rb + (size_t)p * D, row_bytes, bar_full + 8 * slot);
+          agg_bulk_load(agg_smem_u32(ring) + slot * row_bytes, Rb + (size_t)p_cur * D, row_bytes, bar_full + 8 * slot);
         }
-        seq += __popc(act);
       }
-      if (lane == 0) {   // end-of-cluster marker
-        const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
-        agg_mbar_wait(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
-        meta[slot] = kMetaEnd;
-        agg_mbar_arrive(bar_full + 8 * slot);
+      seq += __popc(act);
+      if (last_in_cluster) {
+        if (lane == 0) {   // end-of-cluster marker
+          const unsigned ms = seq % kRingSlots, mg = seq / kRingSlots;
+          agg_mbar_wait(bar_empty + 8 * ms, (mg & 1u) ^ 1u);
+          meta[ms] = kMetaEnd;
+          agg_mbar_arrive(bar_full + 8 * ms);
+        }
+        seq += 1;
+        __syncwarp();
       }
-      seq += 1;
-      __syncwarp();
+      k = nk; i0 = ni0; beg = nbeg; end = nend; p_cur = p_nxt; m_cur = m_nxt;
     }
     return;
   }
@@ -691,7 +714,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   // >= ~2 CTAs per SM (single-image calls) -- batched calls keep every cluster of a group in one CTA
   const int threads = 32 + (int)align_up((size_t)(D / 4), 32);
   int k_per_cta = K;
-  while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 2 * 148) k_per_cta = (k_per_cta + 1) / 2;
+  while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 4 * 148) k_per_cta = (k_per_cta + 1) / 2;
   const dim3 agrid(ng, (K + k_per_cta - 1) / k_per_cta);
   const size_t asmem = (size_t)kRingSlots * D * 4 + kRingSlots * 4 + 2 * kRingSlots * 8 + 13 * kSegGroup * 8 + 64;
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);

@@ -758,20 +758,32 @@ merge_topk_kernel(const float* __restrict__ d2p, const long long* __restrict__ i
 // ------------------------------------------------------------------------------------------------
 // host side
 struct KnnLayout {
-  SelState sel; float* qn; float* rn; int* flags; size_t total;
+  SelState sel[2];   // two query blocks can be in flight (one per internal stream)
+  float* qn; float* rn; int* flags; int block_rows; int n_blocks; size_t total;
 };
 static KnnLayout carve_knn(void* ws, int Nq, int Nr) {
   Carver c(ws);
   KnnLayout L;
-  const int rows = Nq < kQueryBlock ? Nq : kQueryBlock;
-  L.sel.tau = c.take<float>(rows);
-  L.sel.cnt = c.take<int>(rows);
-  L.sel.cand_d2 = c.take<float>((size_t)rows * kCandCap);
-  L.sel.cand_idx = c.take<int>((size_t)rows * kCandCap);
-  L.sel.overflow = c.take<int>(1);
+  // query blocks: bounded by kQueryBlock rows (workspace) and, above 4096 queries, at least two of them so that one
+  // block's refine / re-score / sort (HBM-bound) overlaps the other block's tensor-core scan on a second stream
+  int nsplit = (Nq + kQueryBlock - 1) / kQueryBlock;
+  if (Nq >= 4096 && nsplit < 2) nsplit = 2;
+  if (nsplit < 1) nsplit = 1;
+  L.block_rows = (int)align_up((size_t)((Nq + nsplit - 1) / nsplit), 256);
+  if (L.block_rows > kQueryBlock) L.block_rows = kQueryBlock;
+  if (L.block_rows < 1) L.block_rows = 1;
+  L.n_blocks = (Nq + L.block_rows - 1) / L.block_rows;
+  for (int i = 0; i < 2; ++i) {
+    const int rows = (i == 0 || L.n_blocks > 1) ? L.block_rows : 0;
+    L.sel[i].tau = c.take<float>(rows);
+    L.sel[i].cnt = c.take<int>(rows);
+    L.sel[i].cand_d2 = c.take<float>((size_t)rows * kCandCap);
+    L.sel[i].cand_idx = c.take<int>((size_t)rows * kCandCap);
+    L.sel[i].overflow = c.take<int>(1);
+  }
   L.qn = c.take<float>(Nq);   // SIMT path only
   L.rn = c.take<float>(Nr);   // SIMT path only
-  L.flags = c.take<int>((Nq + kQueryBlock - 1) / kQueryBlock + 1);
+  L.flags = c.take<int>(L.n_blocks + 1);
   L.total = c.total();
   return L;
 }
@@ -829,7 +841,8 @@ struct HostFeed {
 };
 struct SubChunk { int c0, c1; int first_round; int last_of_round; int final_pass; };
 
-static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const KnnLayout& L, int q_row0, int rows, int Nr,
+struct BlockCtx { SelState sel; const float* qn; const float* rn; };
+static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockCtx& L, int q_row0, int rows, int Nr,
                      int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
                      cudaStream_t st, const HostFeed* feed = nullptr) {
   // tensor-core path: select k + margin by the approximate distances, re-score those exactly, keep k
@@ -932,13 +945,15 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
     set_error("knn: workspace %zu < required %zu", workspace_bytes, L.total);
     return SEGVLAD_EWORKSPACE;
   }
-  const int n_blocks = (Nq + kQueryBlock - 1) / kQueryBlock;
+  const int n_blocks = L.n_blocks, QB = L.block_rows;
+  SV_REQUIRE(n_blocks <= 64, "knn: too many query blocks (%d)", n_blocks);
+  BlockCtx ctx[2] = {{L.sel[0], L.qn, L.rn}, {L.sel[1], L.qn, L.rn}};
   if (Nr == 0) {  // nothing to search: pad like faiss
     for (int b = 0; b < n_blocks; ++b) {
-      const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
-      sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, 0);
+      const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
+      sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel[0], rows, 0);
       SV_CHECK_LAUNCH();
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, k, 1, row_offset, q0, d2_out, idx_out);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel[0], k, 1, row_offset, q0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
     }
     return SEGVLAD_OK;
@@ -949,24 +964,44 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
     row_norms_kernel<<<(Nr + 7) / 8, 256, 0, st>>>(sa->r, Nr, D, L.rn);
     SV_CHECK_LAUNCH();
   }
+  // two internal streams when there are >= 2 query blocks and the bank is already resident
+  static cudaStream_t aux[2] = {nullptr, nullptr};
+  const bool dual = n_blocks >= 2 && feed == nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  if (dual) {
+    for (int i = 0; i < 2; ++i)
+      if (!aux[i]) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+    SV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    SV_CHECK_CUDA(cudaEventRecord(ev_fork, st));
+    for (int i = 0; i < 2; ++i) SV_CHECK_CUDA(cudaStreamWaitEvent(aux[i], ev_fork, 0));
+  }
   for (int b = 0; b < n_blocks; ++b) {
-    const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
-    int rc = run_block(tc, ta, sa, L, q0, rows, Nr, D, k, row_offset, false, d2_out, idx_out, st,
+    const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
+    const int si = dual ? (b & 1) : 0;
+    cudaStream_t bs = dual ? aux[si] : st;
+    int rc = run_block(tc, ta, sa, ctx[si], q0, rows, Nr, D, k, row_offset, false, d2_out, idx_out, bs,
                        b == 0 ? feed : nullptr);   // after the first query block the bank is resident
     if (rc) return rc;
-    SV_CHECK_CUDA(cudaMemcpyAsync(L.flags + b, L.sel.overflow, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    SV_CHECK_CUDA(cudaMemcpyAsync(L.flags + b, ctx[si].sel.overflow, sizeof(int), cudaMemcpyDeviceToDevice, bs));
+  }
+  if (dual) {
+    for (int i = 0; i < 2; ++i) {
+      SV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+      SV_CHECK_CUDA(cudaEventRecord(ev_join[i], aux[i]));
+      SV_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join[i], 0));
+    }
   }
   int hflags[64];
-  SV_REQUIRE(n_blocks <= 64, "knn: too many query blocks (%d)", n_blocks);
   SV_CHECK_CUDA(cudaMemcpyAsync(hflags, L.flags, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st));
   SV_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (dual) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join[0]); cudaEventDestroy(ev_join[1]); }
   for (int b = 0; b < n_blocks; ++b) {
     if (!hflags[b]) continue;
-    const int q0 = b * kQueryBlock, rows = (Nq - q0) < kQueryBlock ? (Nq - q0) : kQueryBlock;
-    int rc = run_block(tc, ta, sa, L, q0, rows, Nr, D, k, row_offset, true, d2_out, idx_out, st);
+    const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
+    int rc = run_block(tc, ta, sa, ctx[0], q0, rows, Nr, D, k, row_offset, true, d2_out, idx_out, st);
     if (rc) return rc;
     int f = 0;
-    SV_CHECK_CUDA(cudaMemcpyAsync(&f, L.sel.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SV_CHECK_CUDA(cudaMemcpyAsync(&f, ctx[0].sel.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     SV_CHECK_CUDA(cudaStreamSynchronize(st));
     if (f) { set_error("knn: candidate overflow in the conservative schedule (internal error)"); return SEGVLAD_EOVERFLOW; }
   }
