@@ -766,8 +766,10 @@ static KnnLayout carve_knn(void* ws, int Nq, int Nr) {
   KnnLayout L;
   // query blocks: bounded by kQueryBlock rows (workspace) and, above 4096 queries, at least two of them so that one
   // block's refine / re-score / sort (HBM-bound) overlaps the other block's tensor-core scan on a second stream
+  // (measured r1: splitting a single block in two to overlap refine/re-score with the other half's tensor-core scan
+  //  on a second stream made the step 10 % SLOWER -- the HBM-bound re-score and the TMA-fed scan contend -- so two
+  //  blocks are only in flight when the query set exceeds kQueryBlock and SEGVLAD_KNN_DUAL=1)
   int nsplit = (Nq + kQueryBlock - 1) / kQueryBlock;
-  if (Nq >= 4096 && nsplit < 2) nsplit = 2;
   if (nsplit < 1) nsplit = 1;
   L.block_rows = (int)align_up((size_t)((Nq + nsplit - 1) / nsplit), 256);
   if (L.block_rows > kQueryBlock) L.block_rows = kQueryBlock;
@@ -966,7 +968,8 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
   }
   // two internal streams when there are >= 2 query blocks and the bank is already resident
   static cudaStream_t aux[2] = {nullptr, nullptr};
-  const bool dual = n_blocks >= 2 && feed == nullptr;
+  const char* denv = getenv("SEGVLAD_KNN_DUAL");
+  const bool dual = n_blocks >= 2 && feed == nullptr && denv && denv[0] == '1';
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   if (dual) {
     for (int i = 0; i < 2; ++i)
