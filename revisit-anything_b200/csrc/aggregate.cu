@@ -56,90 +56,169 @@ __global__ void normalize_centers_kernel(const float* __restrict__ c, int K, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Assignment + residual rows, tokens in the reference's [D, N] layout (lane = token => coalesced).
-__global__ void __launch_bounds__(kAssignWarps * 32)
+// Assignment + residual rows, tokens in the reference's [D, N] layout.
+// v2 (r1: v0 streamed the centre table through L1 with 9 load instructions per 32 FFMAs and ran at ~3 TFLOP/s):
+// a register-tiled fp32 GEMM.  CTA = 128 tokens x one 32-cluster chunk at a time, 128 threads; thread (tg, kg) owns
+// 8 tokens x 4 clusters (32 accumulators); per channel it issues 2 LDS.128 (tokens) + 1 LDS.128 (centres) for
+// 32 FFMAs.  x and c_hat tiles ([16 ch][128 tok], [16 ch][32 k]) are staged with cp.async, double buffered.
+// Summation order per (token, cluster): channels ascending, fp32 FMA (the reference's SGEMM is not bit-reproducible;
+// labels are compared where the fp64 margin exceeds 1e-5).
+constexpr int kAsgTok = 128;   // tokens per CTA
+constexpr int kAsgDc = 16;     // channels per pipeline stage
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+__global__ void __launch_bounds__(128)
 assign_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __restrict__ centers,
                  const float* __restrict__ chatT, int K, int Kp, int prenorm, float* __restrict__ R,
                  int* __restrict__ labels) {
-  const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kTokTile;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int p = p0 + lane;
-  const bool valid = p < N;
+  __shared__ __align__(16) float s_x[2][kAsgDc][kAsgTok];
+  __shared__ __align__(16) float s_c[2][kAsgDc][32];
+  __shared__ float s_best[8][kAsgTok];
+  __shared__ int s_besti[8][kAsgTok];
+  __shared__ float s_nrm[kAsgTok];
+  __shared__ int s_lab[kAsgTok];
+  __shared__ float s_t[4][32][33];
+  const int b = blockIdx.y, p0 = blockIdx.x * kAsgTok;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tg = tid & 15, kg = tid >> 4;          // token group (8 tokens), cluster group (4 clusters)
   const float* tok = tokens + (size_t)b * D * N;
-  const int dchunk = (D + kAssignWarps - 1) / kAssignWarps;
-  const int d0 = min(D, w * dchunk), d1 = min(D, d0 + dchunk);
+  const bool vec_ok = (N % 4 == 0) && (p0 + kAsgTok <= N);   // 16-byte aligned, fully inside: cp.async 16 B
+  const bool vec2_ok = (N % 2 == 0);
 
-  __shared__ float s_part[kAssignWarps][32][33];
-  __shared__ float s_ss[kAssignWarps][32];
-  __shared__ float s_nrm[32];
-  __shared__ int s_lab[32];
+  auto stage = [&](int buf, int d0, int kc) {
+    // x tile: kAsgDc rows x 128 tokens
+    if (vec_ok) {
+      for (int i = tid; i < kAsgDc * (kAsgTok / 4); i += 128) {
+        const int r = i / (kAsgTok / 4), c4 = i % (kAsgTok / 4);
+        const int d = d0 + r;
+        if (d < D) cp_async16(&s_x[buf][r][c4 * 4], tok + (size_t)d * N + p0 + c4 * 4);
+        else *reinterpret_cast<float4*>(&s_x[buf][r][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else if (vec2_ok) {    // N even (1530 = 34 x 45): rows are 8-byte aligned
+      for (int i = tid; i < kAsgDc * (kAsgTok / 2); i += 128) {
+        const int r = i / (kAsgTok / 2), c2 = i % (kAsgTok / 2);
+        const int d = d0 + r, p = p0 + c2 * 2;
+        if (d < D && p + 1 < N) cp_async8(&s_x[buf][r][c2 * 2], tok + (size_t)d * N + p);
+        else {
+          s_x[buf][r][c2 * 2] = (d < D && p < N) ? tok[(size_t)d * N + p] : 0.f;
+          s_x[buf][r][c2 * 2 + 1] = 0.f;
+        }
+      }
+    } else {
+      for (int i = tid; i < kAsgDc * kAsgTok; i += 128) {
+        const int r = i / kAsgTok, c = i % kAsgTok;
+        const int d = d0 + r, p = p0 + c;
+        if (d < D && p < N) cp_async4(&s_x[buf][r][c], tok + (size_t)d * N + p);
+        else s_x[buf][r][c] = 0.f;
+      }
+    }
+    // centre tile: kAsgDc rows x 32 clusters (chatT is zero padded to Kp = multiple of 32)
+    {
+      const int r = tid / 8, c4 = tid % 8;
+      const int d = d0 + r;
+      if (d < D) cp_async16(&s_c[buf][r][c4 * 4], chatT + (size_t)d * Kp + kc + c4 * 4);
+      else *reinterpret_cast<float4*>(&s_c[buf][r][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
 
-  float ss = 0.f, bestv = -INFINITY;
-  int besti = 0;
+  float ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ss[i] = 0.f;
+  float bestv[8];
+  int besti[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { bestv[i] = -INFINITY; besti[i] = 0; }
+  const int n_ch = (D + kAsgDc - 1) / kAsgDc;
   for (int kc = 0; kc < K; kc += 32) {
-    float acc[32];
+    float acc[8][4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-    for (int d = d0; d < d1; ++d) {
-      float x = valid ? __ldg(tok + (size_t)d * N + p) : 0.f;
-      if (kc == 0) ss = fmaf(x, x, ss);
-      const float4* cr = reinterpret_cast<const float4*>(chatT + (size_t)d * Kp + kc);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 cv = __ldg(cr + j);
-        acc[4 * j + 0] = fmaf(x, cv.x, acc[4 * j + 0]);
-        acc[4 * j + 1] = fmaf(x, cv.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(x, cv.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(x, cv.w, acc[4 * j + 3]);
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    stage(0, 0, kc);
+    for (int c = 0; c < n_ch; ++c) {
+      const int buf = c & 1;
+      if (c + 1 < n_ch) { stage(buf ^ 1, (c + 1) * kAsgDc, kc); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kAsgDc; ++r) {
+        const float4 x0 = *reinterpret_cast<const float4*>(&s_x[buf][r][tg * 8]);
+        const float4 x1 = *reinterpret_cast<const float4*>(&s_x[buf][r][tg * 8 + 4]);
+        const float4 cv = *reinterpret_cast<const float4*>(&s_c[buf][r][kg * 4]);
+        const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i][0] = fmaf(xs[i], cv.x, acc[i][0]);
+          acc[i][1] = fmaf(xs[i], cv.y, acc[i][1]);
+          acc[i][2] = fmaf(xs[i], cv.z, acc[i][2]);
+          acc[i][3] = fmaf(xs[i], cv.w, acc[i][3]);
+          if (kc == 0 && kg == 0) ss[i] = fmaf(xs[i], xs[i], ss[i]);
+        }
       }
+      __syncthreads();
     }
+    // per-thread best over its 4 clusters (ascending k, strict '>' => first index on ties)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) s_part[w][j][lane] = acc[j];
-    if (kc == 0) s_ss[w][lane] = ss;
-    __syncthreads();
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int kk = 0; kk < 32 / kAssignWarps; ++kk) {
-      int k = w * (32 / kAssignWarps) + kk;
-      float t = 0.f;
-#pragma unroll
-      for (int ww = 0; ww < kAssignWarps; ++ww) t += s_part[ww][k][lane];
-      s_part[0][k][lane] = t;  // distinct k per warp: no hazard with the reads above
-    }
-    __syncthreads();
-    if (w == 0) {
-      for (int k = 0; k < 32 && kc + k < K; ++k) {
-        float v = s_part[0][k][lane];
-        if (v > bestv) { bestv = v; besti = kc + k; }  // strict '>' => first index on ties (torch.argmax)
+      for (int j = 0; j < 4; ++j) {
+        const int k = kc + kg * 4 + j;
+        if (k < K && acc[i][j] > bestv[i]) { bestv[i] = acc[i][j]; besti[i] = k; }
       }
-    }
-    __syncthreads();
   }
-  if (w == 0) {
-    float t = 0.f;
+  // combine the 8 cluster groups per token (ascending cluster order, strict '>')
 #pragma unroll
-    for (int ww = 0; ww < kAssignWarps; ++ww) t += s_ss[ww][lane];
-    s_nrm[lane] = prenorm ? 1.0f : fmaxf(sqrtf(t), kEpsF);
-    s_lab[lane] = besti;
-    if (valid) labels[(size_t)b * N + p] = besti;
+  for (int i = 0; i < 8; ++i) { s_best[kg][tg * 8 + i] = bestv[i]; s_besti[kg][tg * 8 + i] = besti[i]; }
+  if (kg == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_nrm[tg * 8 + i] = prenorm ? 1.0f : fmaxf(sqrtf(ss[i]), kEpsF);
+  __syncthreads();
+  {
+    const int t = tid;   // one thread per token
+    float bv = -INFINITY;
+    int bi = 0;
+    // per-chunk winners are ordered by cluster inside a chunk group; scanning kg ascending keeps the lowest index
+    // only if ties across groups resolve to the smaller k: compare values, on equality keep the smaller index
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) {
+      const float v = s_best[g8][t];
+      const int ki = s_besti[g8][t];
+      if (v > bv || (v == bv && ki < bi)) { bv = v; bi = ki; }
+    }
+    s_lab[t] = bi;
+    if (p0 + t < N) labels[(size_t)b * N + p0 + t] = bi;
   }
   __syncthreads();
-  // residual rows, transposed to token-major through a padded smem tile (per warp, its own d slice)
-  const float nrm = s_nrm[lane];
-  for (int dd = d0; dd < d1; dd += 32) {
-#pragma unroll 4
+  // residual rows: warp w handles tokens [32w, 32w+32) for all channels, transposed through a padded tile
+  const int p = p0 + w * 32 + lane;
+  const bool valid = p < N;
+  const float nrm = s_nrm[w * 32 + lane];
+  for (int dd = 0; dd < D; dd += 32) {
+#pragma unroll 8
     for (int r = 0; r < 32; ++r) {
-      int d = dd + r;
-      float x = (d < d1 && valid) ? __ldg(tok + (size_t)d * N + p) : 0.f;
-      s_part[w][r][lane] = x / nrm;
+      const int d = dd + r;
+      const float x = (d < D && valid) ? __ldg(tok + (size_t)d * N + p) : 0.f;
+      s_t[w][r][lane] = x / nrm;
     }
     __syncwarp();
     const int d = dd + lane;
-    if (d < d1) {
+    if (d < D) {
       for (int t = 0; t < 32; ++t) {
-        int pp = p0 + t;
+        const int pp = p0 + w * 32 + t;
         if (pp < N)
-          R[((size_t)b * N + pp) * D + d] = s_part[w][lane][t] - __ldg(centers + (size_t)s_lab[t] * D + d);
+          R[((size_t)b * N + pp) * D + d] = s_t[w][lane][t] - __ldg(centers + (size_t)s_lab[w * 32 + t] * D + d);
       }
     }
     __syncwarp();
@@ -384,6 +463,11 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     for (int i = 0; i < kRingSlots; ++i) { agg_mbar_init(bar_full + 8 * i, 1); agg_mbar_init(bar_empty + 8 * i, n_cwarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  double* s_rowinv = s_scale + kSegGroup;   // 1 / max(sqrt(#non-empty clusters of the segment), eps), loaded once
+  if (tid >= 32 && tid < 32 + kSegGroup) {
+    const int j = tid - 32;
+    s_rowinv[j] = (j < ns) ? 1.0 / fmax(sqrt((double)cpred[s0 + j]), kEpsD) : 0.0;
+  }
   __syncthreads();
 
   if (warp == 0) {
@@ -537,8 +621,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       double sc = 0.0;
       if (t < ns) {
         norms[(size_t)(s0 + t) * K + k] = nrm;
-        const double rown = fmax(sqrt((double)cpred[s0 + t]), kEpsD);
-        sc = (1.0 / fmax(nrm, kEpsD)) * (1.0 / rown);
+        sc = (1.0 / fmax(nrm, kEpsD)) * s_rowinv[t];
       }
       s_scale[t] = sc;
     }
@@ -707,8 +790,8 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     normalize_centers_kernel<<<K, 256, 0, st>>>(centers, K, D, L.chatT, Kp);
     SV_CHECK_LAUNCH();
     if (layout == SEGVLAD_TOKENS_DN) {
-      dim3 grid((N + kTokTile - 1) / kTokTile, B);
-      assign_dn_kernel<<<grid, kAssignWarps * 32, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
+      dim3 grid((N + kAsgTok - 1) / kAsgTok, B);
+      assign_dn_kernel<<<grid, 128, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
     } else {
       dim3 grid((N + 7) / 8, B);
       assign_nd_kernel<<<grid, 256, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
@@ -734,7 +817,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 4 * 148) k_per_cta = (k_per_cta + 1) / 2;
   const dim3 agrid(ng, (K + k_per_cta - 1) / k_per_cta);
   const size_t asmem = (size_t)kRingSlots * D * 4 + kRingSlots * kSegGroup * 4 + kRingSlots * 4 + 2 * kRingSlots * 8 +
-                       13 * kSegGroup * 8 + 64;
+                       14 * kSegGroup * 8 + 64;
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   if (out_dtype == SEGVLAD_OUT_F64) {
     SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
