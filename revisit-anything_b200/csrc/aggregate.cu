@@ -25,9 +25,6 @@ namespace segvlad {
 constexpr int kSegGroup = 8;       // segments per aggregate CTA (register tile: 8 x 4 accumulators / thread)
 constexpr int kFlushEvery = 16;    // fp32 partial sums are promoted to the fp64 accumulators every 16 rows
 constexpr int kRingSlots = 32;     // residual-row ring (one slot per producer lane)
-constexpr unsigned kMetaEnd = 0xFFFFFFFFu;
-constexpr int kTokTile = 32;       // tokens per assign CTA
-constexpr int kAssignWarps = 8;
 constexpr float kEpsF = 1e-12f;
 constexpr double kEpsD = 1e-12;
 
@@ -78,40 +75,39 @@ __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
 
+constexpr int kAsgSplit = 8;   // channel splits (split-K) -> enough CTAs for small batches; summed in fixed order
+
+// Stage 1: partial dot products over one channel range.  grid (token tiles, B, kAsgSplit), 128 threads.
+//   part[((b*kAsgSplit + split)*N + p)*Kp + k] = sum_{d in range} x[d][p] * c_hat[k][d];   ssq likewise for ||x||^2
 __global__ void __launch_bounds__(128)
-assign_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __restrict__ centers,
-                 const float* __restrict__ chatT, int K, int Kp, int prenorm, float* __restrict__ R,
-                 int* __restrict__ labels) {
+assign_partial_kernel(const float* __restrict__ tokens, int N, int D, const float* __restrict__ chatT, int K, int Kp,
+                      float* __restrict__ part, float* __restrict__ ssq) {
   __shared__ __align__(16) float s_x[2][kAsgDc][kAsgTok];
   __shared__ __align__(16) float s_c[2][kAsgDc][32];
-  __shared__ float s_best[8][kAsgTok];
-  __shared__ int s_besti[8][kAsgTok];
-  __shared__ float s_nrm[kAsgTok];
-  __shared__ int s_lab[kAsgTok];
-  __shared__ float s_t[4][32][33];
-  const int b = blockIdx.y, p0 = blockIdx.x * kAsgTok;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int b = blockIdx.y, p0 = blockIdx.x * kAsgTok, split = blockIdx.z;
+  const int tid = threadIdx.x;
   const int tg = tid & 15, kg = tid >> 4;          // token group (8 tokens), cluster group (4 clusters)
   const float* tok = tokens + (size_t)b * D * N;
+  const int dper = ((D + kAsgSplit - 1) / kAsgSplit + kAsgDc - 1) / kAsgDc * kAsgDc;
+  const int d_lo = min(D, split * dper), d_hi = min(D, d_lo + dper);
   const bool vec_ok = (N % 4 == 0) && (p0 + kAsgTok <= N);   // 16-byte aligned, fully inside: cp.async 16 B
   const bool vec2_ok = (N % 2 == 0);
 
   auto stage = [&](int buf, int d0, int kc) {
-    // x tile: kAsgDc rows x 128 tokens
     if (vec_ok) {
       for (int i = tid; i < kAsgDc * (kAsgTok / 4); i += 128) {
         const int r = i / (kAsgTok / 4), c4 = i % (kAsgTok / 4);
         const int d = d0 + r;
-        if (d < D) cp_async16(&s_x[buf][r][c4 * 4], tok + (size_t)d * N + p0 + c4 * 4);
+        if (d < d_hi) cp_async16(&s_x[buf][r][c4 * 4], tok + (size_t)d * N + p0 + c4 * 4);
         else *reinterpret_cast<float4*>(&s_x[buf][r][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else if (vec2_ok) {    // N even (1530 = 34 x 45): rows are 8-byte aligned
       for (int i = tid; i < kAsgDc * (kAsgTok / 2); i += 128) {
         const int r = i / (kAsgTok / 2), c2 = i % (kAsgTok / 2);
         const int d = d0 + r, p = p0 + c2 * 2;
-        if (d < D && p + 1 < N) cp_async8(&s_x[buf][r][c2 * 2], tok + (size_t)d * N + p);
+        if (d < d_hi && p + 1 < N) cp_async8(&s_x[buf][r][c2 * 2], tok + (size_t)d * N + p);
         else {
-          s_x[buf][r][c2 * 2] = (d < D && p < N) ? tok[(size_t)d * N + p] : 0.f;
+          s_x[buf][r][c2 * 2] = (d < d_hi && p < N) ? tok[(size_t)d * N + p] : 0.f;
           s_x[buf][r][c2 * 2 + 1] = 0.f;
         }
       }
@@ -119,15 +115,14 @@ assign_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __
       for (int i = tid; i < kAsgDc * kAsgTok; i += 128) {
         const int r = i / kAsgTok, c = i % kAsgTok;
         const int d = d0 + r, p = p0 + c;
-        if (d < D && p < N) cp_async4(&s_x[buf][r][c], tok + (size_t)d * N + p);
+        if (d < d_hi && p < N) cp_async4(&s_x[buf][r][c], tok + (size_t)d * N + p);
         else s_x[buf][r][c] = 0.f;
       }
     }
-    // centre tile: kAsgDc rows x 32 clusters (chatT is zero padded to Kp = multiple of 32)
     {
       const int r = tid / 8, c4 = tid % 8;
       const int d = d0 + r;
-      if (d < D) cp_async16(&s_c[buf][r][c4 * 4], chatT + (size_t)d * Kp + kc + c4 * 4);
+      if (d < d_hi) cp_async16(&s_c[buf][r][c4 * 4], chatT + (size_t)d * Kp + kc + c4 * 4);
       else *reinterpret_cast<float4*>(&s_c[buf][r][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     cp_async_commit();
@@ -136,21 +131,18 @@ assign_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __
   float ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) ss[i] = 0.f;
-  float bestv[8];
-  int besti[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { bestv[i] = -INFINITY; besti[i] = 0; }
-  const int n_ch = (D + kAsgDc - 1) / kAsgDc;
+  const int n_ch = (d_hi - d_lo + kAsgDc - 1) / kAsgDc;
+  float* pb = part + ((size_t)b * kAsgSplit + split) * N * Kp;
   for (int kc = 0; kc < K; kc += 32) {
     float acc[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    stage(0, 0, kc);
+    if (n_ch > 0) stage(0, d_lo, kc);
     for (int c = 0; c < n_ch; ++c) {
       const int buf = c & 1;
-      if (c + 1 < n_ch) { stage(buf ^ 1, (c + 1) * kAsgDc, kc); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      if (c + 1 < n_ch) { stage(buf ^ 1, d_lo + (c + 1) * kAsgDc, kc); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < kAsgDc; ++r) {
@@ -169,59 +161,72 @@ assign_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __
       }
       __syncthreads();
     }
-    // per-thread best over its 4 clusters (ascending k, strict '>' => first index on ties)
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kc + kg * 4 + j;
-        if (k < K && acc[i][j] > bestv[i]) { bestv[i] = acc[i][j]; besti[i] = k; }
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int p = p0 + tg * 8 + i;
+      if (p < N) *reinterpret_cast<float4*>(pb + (size_t)p * Kp + kc + kg * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
   }
-  // combine the 8 cluster groups per token (ascending cluster order, strict '>')
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { s_best[kg][tg * 8 + i] = bestv[i]; s_besti[kg][tg * 8 + i] = besti[i]; }
   if (kg == 0)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s_nrm[tg * 8 + i] = prenorm ? 1.0f : fmaxf(sqrtf(ss[i]), kEpsF);
-  __syncthreads();
-  {
-    const int t = tid;   // one thread per token
-    float bv = -INFINITY;
-    int bi = 0;
-    // per-chunk winners are ordered by cluster inside a chunk group; scanning kg ascending keeps the lowest index
-    // only if ties across groups resolve to the smaller k: compare values, on equality keep the smaller index
+    for (int i = 0; i < 8; ++i) {
+      const int p = p0 + tg * 8 + i;
+      if (p < N) ssq[((size_t)b * kAsgSplit + split) * N + p] = ss[i];
+    }
+}
+
+// Stage 2: one thread per token: sum the split partials (ascending split), argmax over clusters (first index on
+// ties), ||x||.
+__global__ void assign_finalize_kernel(const float* __restrict__ part, const float* __restrict__ ssq, int N, int K, int Kp,
+                                       int prenorm, int* __restrict__ labels, float* __restrict__ nrm_out) {
+  const int b = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  float bestv = -INFINITY;
+  int besti = 0;
+  for (int k = 0; k < K; ++k) {
+    float v = 0.f;
 #pragma unroll
-    for (int g8 = 0; g8 < 8; ++g8) {
-      const float v = s_best[g8][t];
-      const int ki = s_besti[g8][t];
-      if (v > bv || (v == bv && ki < bi)) { bv = v; bi = ki; }
-    }
-    s_lab[t] = bi;
-    if (p0 + t < N) labels[(size_t)b * N + p0 + t] = bi;
+    for (int s2 = 0; s2 < kAsgSplit; ++s2) v += part[(((size_t)b * kAsgSplit + s2) * N + p) * Kp + k];
+    if (v > bestv) { bestv = v; besti = k; }
   }
-  __syncthreads();
-  // residual rows: warp w handles tokens [32w, 32w+32) for all channels, transposed through a padded tile
-  const int p = p0 + w * 32 + lane;
+  float t = 0.f;
+#pragma unroll
+  for (int s2 = 0; s2 < kAsgSplit; ++s2) t += ssq[((size_t)b * kAsgSplit + s2) * N + p];
+  labels[(size_t)b * N + p] = besti;
+  nrm_out[(size_t)b * N + p] = prenorm ? 1.0f : fmaxf(sqrtf(t), kEpsF);
+}
+
+// Stage 3: residual rows r = x / ||x|| - c[label], transposed to token-major.  grid (N/32, B, D/256); 8 warps, each
+// a 32-channel slab of 32 tokens through a padded smem tile.
+__global__ void __launch_bounds__(256)
+residual_dn_kernel(const float* __restrict__ tokens, int N, int D, const float* __restrict__ centers,
+                   const int* __restrict__ labels, const float* __restrict__ nrm_in, float* __restrict__ R) {
+  __shared__ float s_t[8][32][33];
+  __shared__ int s_lab[32];
+  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int p = p0 + lane;
   const bool valid = p < N;
-  const float nrm = s_nrm[w * 32 + lane];
-  for (int dd = 0; dd < D; dd += 32) {
+  const float* tok = tokens + (size_t)b * D * N;
+  if (w == 0) s_lab[lane] = valid ? labels[(size_t)b * N + p] : 0;
+  const float nrm = valid ? nrm_in[(size_t)b * N + p] : 1.f;
+  __syncthreads();
+  const int dd = blockIdx.z * 256 + w * 32;
+  if (dd >= D) return;
 #pragma unroll 8
-    for (int r = 0; r < 32; ++r) {
-      const int d = dd + r;
-      const float x = (d < D && valid) ? __ldg(tok + (size_t)d * N + p) : 0.f;
-      s_t[w][r][lane] = x / nrm;
+  for (int r = 0; r < 32; ++r) {
+    const int d = dd + r;
+    const float x = (d < D && valid) ? __ldg(tok + (size_t)d * N + p) : 0.f;
+    s_t[w][r][lane] = x / nrm;
+  }
+  __syncwarp();
+  const int d = dd + lane;
+  if (d < D) {
+#pragma unroll 4
+    for (int t = 0; t < 32; ++t) {
+      const int pp = p0 + t;
+      if (pp < N) R[((size_t)b * N + pp) * D + d] = s_t[w][lane][t] - __ldg(centers + (size_t)s_lab[t] * D + d);
     }
-    __syncwarp();
-    const int d = dd + lane;
-    if (d < D) {
-      for (int t = 0; t < 32; ++t) {
-        const int pp = p0 + w * 32 + t;
-        if (pp < N)
-          R[((size_t)b * N + pp) * D + d] = s_t[w][lane][t] - __ldg(centers + (size_t)s_lab[w * 32 + t] * D + d);
-      }
-    }
-    __syncwarp();
   }
 }
 
@@ -330,16 +335,36 @@ __global__ void superseg_union_kernel(const uint32_t* __restrict__ mem, const ui
   }
 }
 
-__global__ void group_transpose_kernel(const uint32_t* __restrict__ sup, const int* __restrict__ grp_seg0,
-                                       const int* __restrict__ grp_nseg, int N, int W,
-                                       uint16_t* __restrict__ memT) {
+// memS[g][i] = membership word (bit j = segment s0+j of group g) of the i-th token of the image IN LABEL-SORTED ORDER
+// (cl_tok), so the aggregate kernel's producer reads token ids and membership words as two independent, coalesced
+// streams.
+__global__ void group_transpose_kernel(const uint32_t* __restrict__ sup, const int* __restrict__ grp_img,
+                                       const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
+                                       const int* __restrict__ cl_tok, int N, int W, uint16_t* __restrict__ memS) {
   const int g = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= N) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int p = cl_tok[(size_t)grp_img[g] * N + i];
   const int s0 = grp_seg0[g], ns = grp_nseg[g];
   unsigned m = 0;
   for (int j = 0; j < ns; ++j) m |= ((sup[(size_t)(s0 + j) * W + (p >> 5)] >> (p & 31)) & 1u) << j;
-  memT[(size_t)g * N + p] = (uint16_t)m;
+  memS[(size_t)g * N + i] = (uint16_t)m;
+}
+
+// cnt[g][k] = number of tokens of cluster k that belong to at least one segment of group g (= ring slots the
+// aggregate kernel will see for (g, k)); one warp per (g, k)
+__global__ void group_counts_kernel(const uint16_t* __restrict__ memS, const int* __restrict__ grp_img,
+                                    const int* __restrict__ cl_ptr, int N, int K, int* __restrict__ cnt) {
+  const int g = blockIdx.x, lane = threadIdx.x & 31;
+  const int b = grp_img[g];
+  for (int k = threadIdx.x >> 5; k < K; k += blockDim.x >> 5) {
+    const int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
+    int c = 0;
+    for (int i = beg + lane; i < end; i += 32) c += memS[(size_t)g * N + i] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[(size_t)g * K + k] = c;
+  }
 }
 
 // predicted #non-empty (segment, cluster) blocks per segment: one warp per segment
@@ -441,8 +466,8 @@ __device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uin
 template <typename OutT>
 __global__ void __launch_bounds__(416, 1)
 aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, const int* __restrict__ cl_tok,
-                 const uint16_t* __restrict__ memT, const int* __restrict__ grp_img,
-                 const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
+                 const uint16_t* __restrict__ memS, const int* __restrict__ grp_cnt,
+                 const int* __restrict__ grp_img, const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
                  const int* __restrict__ cpred, int N, int D, int K, int k_per_cta, OutT* __restrict__ out,
                  double* __restrict__ norms) {
   extern __shared__ __align__(128) unsigned char agg_smem[];
@@ -473,33 +498,22 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   if (warp == 0) {
     // ================= producer warp =================
     const int* toks = cl_tok + (size_t)b * N;
-    const uint16_t* mrow = memT + (size_t)g * N;
+    const uint16_t* mrow = memS + (size_t)g * N;
     const float* Rb = R + (size_t)b * N * D;
+    // The CTA's tokens are the contiguous range [cl_ptr[k0], cl_ptr[k1]) of the label-sorted list: the producer walks
+    // it in windows of 32 (lane = token) regardless of cluster boundaries -- the consumers know how many rows each
+    // cluster contributes (grp_cnt).  Token ids and membership words are independent coalesced loads, prefetched one
+    // window ahead.  A window is issued in 4 sub-batches of 8 lanes so that slot re-use is waited for at quarter-ring
+    // granularity.
+    const int i_beg = cl_ptr[(size_t)b * (K + 1) + k0], i_end = cl_ptr[(size_t)b * (K + 1) + k1];
     unsigned seq = 0;   // ring sequence number of the next slot (warp-uniform)
-    // software-pipelined window walk: the (token id -> membership word) loads of window w+1 are in flight while
-    // window w is issued; a window is issued in 4 sub-batches of 8 lanes so that slot re-use is waited for at a
-    // quarter-ring granularity (a whole-warp batch would need the entire ring drained before every batch)
-    int k = k0;
-    int beg = cl_ptr[(size_t)b * (K + 1) + k], end = cl_ptr[(size_t)b * (K + 1) + k + 1];
-    int i0 = beg;
     int p_cur = 0;
     unsigned m_cur = 0;
-    if (i0 + lane < end) { p_cur = toks[i0 + lane]; m_cur = mrow[p_cur]; }
-    while (k < k1) {
-      const bool last_in_cluster = (i0 + 32 >= end);
-      int nk = k, ni0 = i0 + 32, nbeg = beg, nend = end;
-      if (last_in_cluster) {
-        nk = k + 1;
-        if (nk < k1) {
-          nbeg = cl_ptr[(size_t)b * (K + 1) + nk];
-          nend = cl_ptr[(size_t)b * (K + 1) + nk + 1];
-          ni0 = nbeg;
-        }
-      }
+    if (i_beg + lane < i_end) { p_cur = toks[i_beg + lane]; m_cur = mrow[i_beg + lane]; }
+    for (int i0 = i_beg; i0 < i_end; i0 += 32) {
       int p_nxt = 0;
       unsigned m_nxt = 0;
-      if (nk < k1 && ni0 + lane < nend) { p_nxt = toks[ni0 + lane]; m_nxt = mrow[p_nxt]; }   // prefetch
-
+      if (i0 + 32 + lane < i_end) { p_nxt = toks[i0 + 32 + lane]; m_nxt = mrow[i0 + 32 + lane]; }   // prefetch
       const unsigned act = __ballot_sync(0xffffffffu, m_cur != 0u);
       const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
       const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
@@ -516,7 +530,6 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();
         }
         if (mine) {
-          meta[slot] = m_cur;
           float4 f0, f1;
           f0.x = (m_cur & 1u) ? 1.f : 0.f;   f0.y = (m_cur & 2u) ? 1.f : 0.f;
           f0.z = (m_cur & 4u) ? 1.f : 0.f;   f0.w = (m_cur & 8u) ? 1.f : 0.f;
@@ -529,17 +542,8 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
         }
       }
       seq += __popc(act);
-      if (last_in_cluster) {
-        if (lane == 0) {   // end-of-cluster marker
-          const unsigned ms = seq % kRingSlots, mg = seq / kRingSlots;
-          agg_mbar_wait(bar_empty + 8 * ms, (mg & 1u) ^ 1u);
-          meta[ms] = kMetaEnd;
-          agg_mbar_arrive(bar_full + 8 * ms);
-        }
-        seq += 1;
-        __syncwarp();
-      }
-      k = nk; i0 = ni0; beg = nbeg; end = nend; p_cur = p_nxt; m_cur = m_nxt;
+      p_cur = p_nxt;
+      m_cur = m_nxt;
     }
     return;
   }
@@ -565,18 +569,17 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   }
   int since = 0;
   unsigned seq = 0;
-  int k = k0;
-  while (k < k1) {
-    const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
-    agg_mbar_wait(bar_full + 8 * slot, gen & 1u);
-    const unsigned m = meta[slot];
-    if (m != kMetaEnd) {
+  for (int k = k0; k < k1; ++k) {
+    const int n_rows = grp_cnt[(size_t)g * K + k];
+    for (int rix = 0; rix < n_rows; ++rix) {
+      const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
+      agg_mbar_wait(bar_full + 8 * slot, gen & 1u);
       const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 b0 = *reinterpret_cast<const float4*>(maskf + slot * kSegGroup);
       const float4 b1 = *reinterpret_cast<const float4*>(maskf + slot * kSegGroup + 4);
       const float2 rlo = make_float2(r.x, r.y), rhi = make_float2(r.z, r.w);
-#define SV_FMA(J, B)                                             \
-      a32[J][0] = __ffma2_rn(make_float2(B, B), rlo, a32[J][0]); \
+#define SV_FMA(J, B)                                               \
+      a32[J][0] = __ffma2_rn(make_float2(B, B), rlo, a32[J][0]);   \
       a32[J][1] = __ffma2_rn(make_float2(B, B), rhi, a32[J][1]);
       SV_FMA(0, b0.x) SV_FMA(1, b0.y) SV_FMA(2, b0.z) SV_FMA(3, b0.w)
       SV_FMA(4, b1.x) SV_FMA(5, b1.y) SV_FMA(6, b1.z) SV_FMA(7, b1.w)
@@ -593,7 +596,6 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
         }
       }
-      continue;
     }
     // end-of-cluster: promote the remaining partial sums
     since = 0;
@@ -604,9 +606,6 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
     }
     // ---- cluster k complete: intra-norm, row scale, store ----
-    __syncwarp();
-    if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
-    ++seq;
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
       double ss = acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1] + acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3];
@@ -635,7 +634,6 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       }
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
     }
-    ++k;
   }
 }
 
@@ -693,7 +691,7 @@ __global__ void mask_to_membership_kernel(const uint8_t* __restrict__ masks, int
 
 // ------------------------------------------------------------------------------------------------
 struct AggLayout {
-  float* chatT; float* R; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT;
+  float* chatT; float* R; float* part; float* ssq; float* nrm; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT; int* gcnt;
   int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
   size_t total;
 };
@@ -705,11 +703,15 @@ static AggLayout carve_agg(void* ws, int B, int N, int D, int K, int S_total) {
   const int max_groups = S_total / kSegGroup + B;  // sum_b ceil(S_b / G) <= S_total/G + B
   L.chatT = c.take<float>((size_t)D * Kp);
   L.R = c.take<float>((size_t)B * N * D);
+  L.part = c.take<float>((size_t)B * kAsgSplit * N * Kp);
+  L.ssq = c.take<float>((size_t)B * kAsgSplit * N);
+  L.nrm = c.take<float>((size_t)B * N);
   L.labels = c.take<int>((size_t)B * N);
   L.cl_ptr = c.take<int>((size_t)B * (K + 1));
   L.cl_tok = c.take<int>((size_t)B * N);
   L.sup = c.take<uint32_t>((size_t)S_total * W);
   L.memT = c.take<uint16_t>((size_t)max_groups * N);
+  L.gcnt = c.take<int>((size_t)max_groups * K);
   L.cpred = c.take<int>(S_total);
   L.norms = c.take<double>((size_t)S_total * K);
   L.seg_off = c.take<int>(B + 1);
@@ -790,8 +792,13 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     normalize_centers_kernel<<<K, 256, 0, st>>>(centers, K, D, L.chatT, Kp);
     SV_CHECK_LAUNCH();
     if (layout == SEGVLAD_TOKENS_DN) {
-      dim3 grid((N + kAsgTok - 1) / kAsgTok, B);
-      assign_dn_kernel<<<grid, 128, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
+      assign_partial_kernel<<<dim3((N + kAsgTok - 1) / kAsgTok, B, kAsgSplit), 128, 0, st>>>(tokens, N, D, L.chatT, K, Kp,
+                                                                                          L.part, L.ssq);
+      SV_CHECK_LAUNCH();
+      assign_finalize_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(L.part, L.ssq, N, K, Kp, prenorm, L.labels, L.nrm);
+      SV_CHECK_LAUNCH();
+      residual_dn_kernel<<<dim3((N + 31) / 32, B, (D + 255) / 256), 256, 0, st>>>(tokens, N, D, centers, L.labels, L.nrm,
+                                                                               L.R);
     } else {
       dim3 grid((N + 7) / 8, B);
       assign_nd_kernel<<<grid, 256, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
@@ -806,7 +813,10 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     SV_CHECK_LAUNCH();
     sup = L.sup;
   }
-  group_transpose_kernel<<<dim3((N + 255) / 256, ng), 256, 0, st>>>(sup, L.grp_seg0, L.grp_nseg, N, W, L.memT);
+  group_transpose_kernel<<<dim3((N + 255) / 256, ng), 256, 0, st>>>(sup, L.grp_img, L.grp_seg0, L.grp_nseg, L.cl_tok, N, W,
+                                                                    L.memT);
+  SV_CHECK_LAUNCH();
+  group_counts_kernel<<<ng, 256, 0, st>>>(L.memT, L.grp_img, L.cl_ptr, N, K, L.gcnt);
   SV_CHECK_LAUNCH();
   nonempty_kernel<<<S_total, 32, 0, st>>>(sup, labels, L.seg_off, B, N, W, L.cpred);
   SV_CHECK_LAUNCH();
@@ -821,14 +831,14 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   if (out_dtype == SEGVLAD_OUT_F64) {
     SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
-    aggregate_kernel<double><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
+    aggregate_kernel<double><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.gcnt, L.grp_img, L.grp_seg0,
                                                            L.grp_nseg, L.cpred, N, D, K, k_per_cta, (double*)out, L.norms);
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
   } else {
     SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
-    aggregate_kernel<float><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.grp_img, L.grp_seg0,
+    aggregate_kernel<float><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.gcnt, L.grp_img, L.grp_seg0,
                                                           L.grp_nseg, L.cpred, N, D, K, k_per_cta, (float*)out, L.norms);
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();

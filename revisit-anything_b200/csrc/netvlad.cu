@@ -12,8 +12,6 @@
 
 namespace segvlad {
 
-constexpr int kNvTile = 64;
-
 // tokens [B][D][N] -> x_hat [B][N][D] (token-major, unit rows)
 __global__ void __launch_bounds__(256)
 nv_normalize_kernel(const float* __restrict__ x, int N, int D, float* __restrict__ xh) {
