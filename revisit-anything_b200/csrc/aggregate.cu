@@ -409,6 +409,9 @@ template <> struct Store4<float> {
   }
 };
 
+// optional timing probe (tests/agg_probe.py): per-CTA cycle counters written by the producer / first consumer warp
+static unsigned long long* g_agg_dbg = nullptr;
+
 // ---- mbarrier / bulk-copy PTX (sm_90+; 1-D TMA bulk copy, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void agg_mbar_init(uint32_t bar, uint32_t count) {
@@ -469,8 +472,9 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
                  const uint16_t* __restrict__ memS, const int* __restrict__ grp_cnt,
                  const int* __restrict__ grp_img, const int* __restrict__ grp_seg0, const int* __restrict__ grp_nseg,
                  const int* __restrict__ cpred, int N, int D, int K, int k_per_cta, OutT* __restrict__ out,
-                 double* __restrict__ norms) {
+                 double* __restrict__ norms, unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char agg_smem[];
+  const long long t_start = clock64();
   const int g = blockIdx.x;
   const int k0 = blockIdx.y * k_per_cta, k1 = min(K, k0 + k_per_cta);
   const int b = grp_img[g], s0 = grp_seg0[g], ns = grp_nseg[g];
@@ -509,6 +513,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     unsigned seq = 0;   // ring sequence number of the next slot (warp-uniform)
     int p_cur = 0;
     unsigned m_cur = 0;
+    long long t_poll = 0, t_issue = 0;
     if (i_beg + lane < i_end) { p_cur = toks[i_beg + lane]; m_cur = mrow[i_beg + lane]; }
     for (int i0 = i_beg; i0 < i_end; i0 += 32) {
       int p_nxt = 0;
@@ -529,6 +534,8 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           if (__all_sync(0xffffffffu, ok)) break;
           if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();
         }
+        const long long t1 = clock64();
+        if (dbg) t_poll += t1 - t0;
         if (mine) {
           float4 f0, f1;
           f0.x = (m_cur & 1u) ? 1.f : 0.f;   f0.y = (m_cur & 2u) ? 1.f : 0.f;
@@ -540,10 +547,16 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
           agg_bulk_load(agg_smem_u32(ring) + slot * row_bytes, Rb + (size_t)p_cur * D, row_bytes, bar_full + 8 * slot);
         }
+        __syncwarp();
+        if (dbg) t_issue += clock64() - t1;
       }
       seq += __popc(act);
       p_cur = p_nxt;
       m_cur = m_nxt;
+    }
+    if (dbg && lane == 0) {
+      unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      o[0] = (unsigned long long)(clock64() - t_start); o[1] = (unsigned long long)t_poll; o[2] = (unsigned long long)t_issue; o[3] = seq;
     }
     return;
   }
@@ -569,42 +582,72 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   }
   int since = 0;
   unsigned seq = 0;
+  long long t_wait = 0, t_epi = 0;
+  const bool probe = dbg != nullptr;
+#define SV_FMA(J, B, RLO, RHI)                                     \
+      a32[J][0] = __ffma2_rn(make_float2(B, B), RLO, a32[J][0]);   \
+      a32[J][1] = __ffma2_rn(make_float2(B, B), RHI, a32[J][1]);
+#define SV_ROW(R, B0, B1)                                                                   \
+      {                                                                                     \
+        const float2 rlo = make_float2(R.x, R.y), rhi = make_float2(R.z, R.w);              \
+        SV_FMA(0, B0.x, rlo, rhi) SV_FMA(1, B0.y, rlo, rhi) SV_FMA(2, B0.z, rlo, rhi) SV_FMA(3, B0.w, rlo, rhi) \
+        SV_FMA(4, B1.x, rlo, rhi) SV_FMA(5, B1.y, rlo, rhi) SV_FMA(6, B1.z, rlo, rhi) SV_FMA(7, B1.w, rlo, rhi) \
+      }
+#define SV_FLUSH()                                                                          \
+      {                                                                                     \
+        since = 0;                                                                          \
+        _Pragma("unroll") for (int j = 0; j < kSegGroup; ++j) {                             \
+          acc[j][0] += (double)a32[j][0].x; acc[j][1] += (double)a32[j][0].y;               \
+          acc[j][2] += (double)a32[j][1].x; acc[j][3] += (double)a32[j][1].y;               \
+          a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);                                    \
+        }                                                                                   \
+      }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = k0; k < k1; ++k) {
     const int n_rows = grp_cnt[(size_t)g * K + k];
-    for (int rix = 0; rix < n_rows; ++rix) {
+    int rix = 0;
+    // two rows per iteration: both barrier probes, all six shared-memory loads and 32 packed FMAs are in flight together
+    for (; rix + 2 <= n_rows; rix += 2) {
+      const unsigned s_a = seq % kRingSlots, g_a = seq / kRingSlots;
+      const unsigned s_b = (seq + 1) % kRingSlots, g_b = (seq + 1) / kRingSlots;
+      long long tw0 = 0;
+      if (probe) tw0 = clock64();
+      agg_mbar_wait(bar_full + 8 * s_a, g_a & 1u);
+      agg_mbar_wait(bar_full + 8 * s_b, g_b & 1u);
+      if (probe) t_wait += clock64() - tw0;
+      const float4 ra = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)s_a * D + d) : zero4;
+      const float4 rb = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)s_b * D + d) : zero4;
+      const float4 a0 = *reinterpret_cast<const float4*>(maskf + s_a * kSegGroup);
+      const float4 a1 = *reinterpret_cast<const float4*>(maskf + s_a * kSegGroup + 4);
+      const float4 c0 = *reinterpret_cast<const float4*>(maskf + s_b * kSegGroup);
+      const float4 c1 = *reinterpret_cast<const float4*>(maskf + s_b * kSegGroup + 4);
+      SV_ROW(ra, a0, a1)
+      SV_ROW(rb, c0, c1)
+      __syncwarp();
+      if (lane == 0) { agg_mbar_arrive(bar_empty + 8 * s_a); agg_mbar_arrive(bar_empty + 8 * s_b); }
+      seq += 2;
+      since += 2;
+      if (since >= kFlushEvery) SV_FLUSH()
+    }
+    if (rix < n_rows) {
       const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
+      long long tw0 = 0;
+      if (probe) tw0 = clock64();
       agg_mbar_wait(bar_full + 8 * slot, gen & 1u);
-      const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (probe) t_wait += clock64() - tw0;
+      const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d) : zero4;
       const float4 b0 = *reinterpret_cast<const float4*>(maskf + slot * kSegGroup);
       const float4 b1 = *reinterpret_cast<const float4*>(maskf + slot * kSegGroup + 4);
-      const float2 rlo = make_float2(r.x, r.y), rhi = make_float2(r.z, r.w);
-#define SV_FMA(J, B)                                               \
-      a32[J][0] = __ffma2_rn(make_float2(B, B), rlo, a32[J][0]);   \
-      a32[J][1] = __ffma2_rn(make_float2(B, B), rhi, a32[J][1]);
-      SV_FMA(0, b0.x) SV_FMA(1, b0.y) SV_FMA(2, b0.z) SV_FMA(3, b0.w)
-      SV_FMA(4, b1.x) SV_FMA(5, b1.y) SV_FMA(6, b1.z) SV_FMA(7, b1.w)
-#undef SV_FMA
+      SV_ROW(r, b0, b1)
       __syncwarp();
       if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
       ++seq;
-      if (++since == kFlushEvery) {
-        since = 0;
-#pragma unroll
-        for (int j = 0; j < kSegGroup; ++j) {
-          acc[j][0] += (double)a32[j][0].x; acc[j][1] += (double)a32[j][0].y;
-          acc[j][2] += (double)a32[j][1].x; acc[j][3] += (double)a32[j][1].y;
-          a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
-        }
-      }
+      ++since;
     }
     // end-of-cluster: promote the remaining partial sums
-    since = 0;
-#pragma unroll
-    for (int j = 0; j < kSegGroup; ++j) {
-      acc[j][0] += (double)a32[j][0].x; acc[j][1] += (double)a32[j][0].y;
-      acc[j][2] += (double)a32[j][1].x; acc[j][3] += (double)a32[j][1].y;
-      a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
-    }
+    long long te0 = 0;
+    if (probe) te0 = clock64();
+    SV_FLUSH()
     // ---- cluster k complete: intra-norm, row scale, store ----
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
@@ -613,16 +656,23 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       if (lane == 0) s_red[cw * kSegGroup + j] = ss;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
-    if (t < kSegGroup) {
+    if (cw == 0) {
+      // 32 lanes: lane = (quarter q, segment j); each sums the partials of warps q, q+4, q+8, ... in ascending order,
+      // then the four quarters are combined by two xor-shuffles (fixed order => deterministic)
+      const int j = lane & 7, q = lane >> 3;
       double tot = 0.0;
-      for (int ww = 0; ww < n_cwarps; ++ww) tot += s_red[ww * kSegGroup + t];
-      const double nrm = sqrt(tot);
-      double sc = 0.0;
-      if (t < ns) {
-        norms[(size_t)(s0 + t) * K + k] = nrm;
-        sc = (1.0 / fmax(nrm, kEpsD)) * s_rowinv[t];
+      for (int ww = q; ww < n_cwarps; ww += 4) tot += s_red[ww * kSegGroup + j];
+      tot += __shfl_xor_sync(0xffffffffu, tot, 8);
+      tot += __shfl_xor_sync(0xffffffffu, tot, 16);
+      if (q == 0) {
+        double sc = 0.0;
+        if (j < ns) {
+          const double nrm = sqrt(tot);
+          norms[(size_t)(s0 + j) * K + k] = nrm;
+          sc = (1.0 / fmax(nrm, kEpsD)) * s_rowinv[j];
+        }
+        s_scale[j] = sc;
       }
-      s_scale[t] = sc;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
 #pragma unroll
@@ -634,6 +684,14 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       }
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
     }
+    if (probe) t_epi += clock64() - te0;
+  }
+#undef SV_FLUSH
+#undef SV_ROW
+#undef SV_FMA
+  if (dbg && tid == 32) {
+    unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    o[4] = (unsigned long long)(clock64() - t_start); o[5] = (unsigned long long)t_wait; o[6] = (unsigned long long)t_epi; o[7] = seq;
   }
 }
 
@@ -832,14 +890,14 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   if (out_dtype == SEGVLAD_OUT_F64) {
     SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
     aggregate_kernel<double><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.gcnt, L.grp_img, L.grp_seg0,
-                                                           L.grp_nseg, L.cpred, N, D, K, k_per_cta, (double*)out, L.norms);
+                                                           L.grp_nseg, L.cpred, N, D, K, k_per_cta, (double*)out, L.norms, g_agg_dbg);
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
   } else {
     SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
     aggregate_kernel<float><<<agrid, threads, asmem, st>>>(R, L.cl_ptr, L.cl_tok, L.memT, L.gcnt, L.grp_img, L.grp_seg0,
-                                                          L.grp_nseg, L.cpred, N, D, K, k_per_cta, (float*)out, L.norms);
+                                                          L.grp_nseg, L.cpred, N, D, K, k_per_cta, (float*)out, L.norms, g_agg_dbg);
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     rownorm_fixup_kernel<float><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (float*)out);
@@ -870,6 +928,9 @@ extern "C" int segvlad_aggregate_residuals(const float* residuals, const int32_t
                           seg_offsets_host, adj, out, out_dtype, nullptr, workspace, workspace_bytes,
                           reinterpret_cast<cudaStream_t>(stream_));
 }
+
+// timing probe: buf = device array of >= 8 * (#aggregate CTAs) uint64, or NULL to disable (not part of the product API)
+extern "C" void segvlad_debug_aggregate_probe(unsigned long long* buf) { segvlad::g_agg_dbg = buf; }
 
 extern "C" int segvlad_mask_to_membership(const uint8_t* masks, int S, int Hm, int Wm, int H, int W, int patch,
                                           uint32_t* member_bits, void* stream_) {
