@@ -24,7 +24,10 @@ namespace segvlad {
 
 constexpr int kSegGroup = 8;       // segments per aggregate CTA (register tile: 8 x 4 accumulators / thread)
 constexpr int kFlushEvery = 16;    // fp32 partial sums are promoted to the fp64 accumulators every 16 rows
-constexpr int kRingSlots = 32;     // residual-row ring (one slot per producer lane)
+constexpr int kRingRows = 32;      // residual rows in flight per CTA (one per producer lane)
+constexpr int kRowsPerSlot = 4;    // rows sharing one full/empty mbarrier pair (r1 probe: per-row mbarrier traffic from
+                                   // 12 consumer warps + producer, ~26 ops/row, was the consumer's bottleneck)
+constexpr int kRingSlots = kRingRows / kRowsPerSlot;
 constexpr float kEpsF = 1e-12f;
 constexpr double kEpsD = 1e-12;
 
@@ -482,14 +485,13 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   const int n_cwarps = (blockDim.x >> 5) - 1;
   const uint32_t row_bytes = (uint32_t)D * 4u;
   float* ring = reinterpret_cast<float*>(agg_smem);
-  float* maskf = reinterpret_cast<float*>(agg_smem + (size_t)kRingSlots * row_bytes);   // [slot][kSegGroup] 0/1
-  unsigned* meta = reinterpret_cast<unsigned*>(maskf + kRingSlots * kSegGroup);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + kRingSlots);
+  float* maskf = reinterpret_cast<float*>(agg_smem + (size_t)kRingRows * row_bytes);   // [row][kSegGroup] 0/1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(maskf + kRingRows * kSegGroup);
   double* s_red = reinterpret_cast<double*>(bars + 2 * kRingSlots);      // [12 warps][kSegGroup]
   double* s_scale = s_red + 12 * kSegGroup;                              // [kSegGroup]
   const uint32_t bar_full = agg_smem_u32(bars), bar_empty = agg_smem_u32(bars + kRingSlots);
   if (tid == 0) {
-    for (int i = 0; i < kRingSlots; ++i) { agg_mbar_init(bar_full + 8 * i, 1); agg_mbar_init(bar_empty + 8 * i, n_cwarps); }
+    for (int i = 0; i < kRingSlots; ++i) { agg_mbar_init(bar_full + 8 * i, kRowsPerSlot); agg_mbar_init(bar_empty + 8 * i, n_cwarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   double* s_rowinv = s_scale + kSegGroup;   // 1 / max(sqrt(#non-empty clusters of the segment), eps), loaded once
@@ -521,7 +523,8 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       if (i0 + 32 + lane < i_end) { p_nxt = toks[i0 + 32 + lane]; m_nxt = mrow[i0 + 32 + lane]; }   // prefetch
       const unsigned act = __ballot_sync(0xffffffffu, m_cur != 0u);
       const unsigned n = seq + __popc(act & ((1u << lane) - 1u));
-      const unsigned slot = n % kRingSlots, gen = n / kRingSlots;
+      const unsigned rrow = n % kRingRows;                               // ring row of this lane's token
+      const unsigned slot = rrow / kRowsPerSlot, gen = n / kRingRows;    // barrier pair / ring generation
 #pragma unroll 1
       for (int sub = 0; sub < 4; ++sub) {
         const bool mine = (m_cur != 0u) && ((lane >> 3) == sub);
@@ -542,10 +545,10 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           f0.z = (m_cur & 4u) ? 1.f : 0.f;   f0.w = (m_cur & 8u) ? 1.f : 0.f;
           f1.x = (m_cur & 16u) ? 1.f : 0.f;  f1.y = (m_cur & 32u) ? 1.f : 0.f;
           f1.z = (m_cur & 64u) ? 1.f : 0.f;  f1.w = (m_cur & 128u) ? 1.f : 0.f;
-          *reinterpret_cast<float4*>(maskf + slot * kSegGroup) = f0;
-          *reinterpret_cast<float4*>(maskf + slot * kSegGroup + 4) = f1;
+          *reinterpret_cast<float4*>(maskf + rrow * kSegGroup) = f0;
+          *reinterpret_cast<float4*>(maskf + rrow * kSegGroup + 4) = f1;
           agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
-          agg_bulk_load(agg_smem_u32(ring) + slot * row_bytes, Rb + (size_t)p_cur * D, row_bytes, bar_full + 8 * slot);
+          agg_bulk_load(agg_smem_u32(ring) + rrow * row_bytes, Rb + (size_t)p_cur * D, row_bytes, bar_full + 8 * slot);
         }
         __syncwarp();
         if (dbg) t_issue += clock64() - t1;
@@ -554,8 +557,13 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       p_cur = p_nxt;
       m_cur = m_nxt;
     }
+    // complete the last, partially filled slot so that its consumers are released
+    if (lane == 0 && (seq % kRowsPerSlot) != 0) {
+      const unsigned slot = (seq % kRingRows) / kRowsPerSlot;
+      for (unsigned i = seq % kRowsPerSlot; i < kRowsPerSlot; ++i) agg_mbar_arrive(bar_full + 8 * slot);
+    }
     if (dbg && lane == 0) {
-      unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+      unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
       o[0] = (unsigned long long)(clock64() - t_start); o[1] = (unsigned long long)t_poll; o[2] = (unsigned long long)t_issue; o[3] = seq;
     }
     return;
@@ -582,7 +590,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   }
   int since = 0;
   unsigned seq = 0;
-  long long t_wait = 0, t_epi = 0;
+  long long t_wait = 0, t_epi = 0, t_e1 = 0, t_e2 = 0, t_e3 = 0;
   const bool probe = dbg != nullptr;
 #define SV_FMA(J, B, RLO, RHI)                                     \
       a32[J][0] = __ffma2_rn(make_float2(B, B), RLO, a32[J][0]);   \
@@ -605,44 +613,27 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = k0; k < k1; ++k) {
     const int n_rows = grp_cnt[(size_t)g * K + k];
-    int rix = 0;
-    // two rows per iteration: both barrier probes, all six shared-memory loads and 32 packed FMAs are in flight together
-    for (; rix + 2 <= n_rows; rix += 2) {
-      const unsigned s_a = seq % kRingSlots, g_a = seq / kRingSlots;
-      const unsigned s_b = (seq + 1) % kRingSlots, g_b = (seq + 1) / kRingSlots;
-      long long tw0 = 0;
-      if (probe) tw0 = clock64();
-      agg_mbar_wait(bar_full + 8 * s_a, g_a & 1u);
-      agg_mbar_wait(bar_full + 8 * s_b, g_b & 1u);
-      if (probe) t_wait += clock64() - tw0;
-      const float4 ra = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)s_a * D + d) : zero4;
-      const float4 rb = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)s_b * D + d) : zero4;
-      const float4 a0 = *reinterpret_cast<const float4*>(maskf + s_a * kSegGroup);
-      const float4 a1 = *reinterpret_cast<const float4*>(maskf + s_a * kSegGroup + 4);
-      const float4 c0 = *reinterpret_cast<const float4*>(maskf + s_b * kSegGroup);
-      const float4 c1 = *reinterpret_cast<const float4*>(maskf + s_b * kSegGroup + 4);
-      SV_ROW(ra, a0, a1)
-      SV_ROW(rb, c0, c1)
-      __syncwarp();
-      if (lane == 0) { agg_mbar_arrive(bar_empty + 8 * s_a); agg_mbar_arrive(bar_empty + 8 * s_b); }
-      seq += 2;
-      since += 2;
-      if (since >= kFlushEvery) SV_FLUSH()
-    }
-    if (rix < n_rows) {
-      const unsigned slot = seq % kRingSlots, gen = seq / kRingSlots;
-      long long tw0 = 0;
-      if (probe) tw0 = clock64();
-      agg_mbar_wait(bar_full + 8 * slot, gen & 1u);
-      if (probe) t_wait += clock64() - tw0;
-      const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)slot * D + d) : zero4;
-      const float4 b0 = *reinterpret_cast<const float4*>(maskf + slot * kSegGroup);
-      const float4 b1 = *reinterpret_cast<const float4*>(maskf + slot * kSegGroup + 4);
+    // rows are consumed in ring order; the full barrier is waited for when a row opens a new slot (every
+    // kRowsPerSlot rows) and the empty barrier is signalled when a row closes one
+#pragma unroll 2
+    for (int rix = 0; rix < n_rows; ++rix) {
+      const unsigned rrow = seq % kRingRows, slot = rrow / kRowsPerSlot;
+      if ((seq % kRowsPerSlot) == 0) {
+        long long tw0 = 0;
+        if (probe) tw0 = clock64();
+        agg_mbar_wait(bar_full + 8 * slot, (seq / kRingRows) & 1u);
+        if (probe) t_wait += clock64() - tw0;
+      }
+      const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)rrow * D + d) : zero4;
+      const float4 b0 = *reinterpret_cast<const float4*>(maskf + rrow * kSegGroup);
+      const float4 b1 = *reinterpret_cast<const float4*>(maskf + rrow * kSegGroup + 4);
       SV_ROW(r, b0, b1)
-      __syncwarp();
-      if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
+      if ((seq % kRowsPerSlot) == kRowsPerSlot - 1) {
+        __syncwarp();
+        if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
+      }
       ++seq;
-      ++since;
+      if (++since >= kFlushEvery) SV_FLUSH()
     }
     // end-of-cluster: promote the remaining partial sums
     long long te0 = 0;
@@ -655,6 +646,8 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       ss = warp_sum(ss);
       if (lane == 0) s_red[cw * kSegGroup + j] = ss;
     }
+    long long tp1 = 0;
+    if (probe) { tp1 = clock64(); t_e1 += tp1 - te0; }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
     if (cw == 0) {
       // 32 lanes: lane = (quarter q, segment j); each sums the partials of warps q, q+4, q+8, ... in ascending order,
@@ -674,7 +667,10 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
         s_scale[j] = sc;
       }
     }
+    long long tp2 = 0;
+    if (probe) { tp2 = clock64(); t_e2 += tp2 - tp1; }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
+    if (probe) t_e3 += clock64() - tp2;
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
       if (j < ns && act_ch) {
@@ -690,8 +686,9 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
 #undef SV_ROW
 #undef SV_FMA
   if (dbg && tid == 32) {
-    unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
     o[4] = (unsigned long long)(clock64() - t_start); o[5] = (unsigned long long)t_wait; o[6] = (unsigned long long)t_epi; o[7] = seq;
+    o[8] = (unsigned long long)t_e1; o[9] = (unsigned long long)t_e2; o[10] = (unsigned long long)t_e3;
   }
 }
 
@@ -884,7 +881,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   int k_per_cta = K;
   while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 4 * 148) k_per_cta = (k_per_cta + 1) / 2;
   const dim3 agrid(ng, (K + k_per_cta - 1) / k_per_cta);
-  const size_t asmem = (size_t)kRingSlots * D * 4 + kRingSlots * kSegGroup * 4 + kRingSlots * 4 + 2 * kRingSlots * 8 +
+  const size_t asmem = (size_t)kRingRows * D * 4 + kRingRows * kSegGroup * 4 + 2 * kRingSlots * 8 +
                        14 * kSegGroup * 8 + 64;
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   if (out_dtype == SEGVLAD_OUT_F64) {
