@@ -24,7 +24,7 @@ namespace segvlad {
 
 constexpr int kSegGroup = 8;       // segments per aggregate CTA (register tile: 8 x 4 accumulators / thread)
 constexpr int kFlushEvery = 16;    // fp32 partial sums are promoted to the fp64 accumulators every 16 rows
-constexpr int kRingRows = 32;      // residual rows in flight per CTA (one per producer lane)
+constexpr int kRingRows = 16;      // residual rows in flight per CTA (the other half of shared memory stages the output)
 constexpr int kRowsPerSlot = 4;    // rows sharing one full/empty mbarrier pair (r1 probe: per-row mbarrier traffic from
                                    // 12 consumer warps + producer, ~26 ops/row, was the consumer's bottleneck)
 constexpr int kRingSlots = kRingRows / kRowsPerSlot;
@@ -415,6 +415,19 @@ template <> struct Store4<float> {
 // optional timing probe (tests/agg_probe.py): per-CTA cycle counters written by the producer / first consumer warp
 static unsigned long long* g_agg_dbg = nullptr;
 
+template <typename OutT> struct Stage4;
+template <> struct Stage4<double> {
+  static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+  }
+};
+template <> struct Stage4<float> {
+  static __device__ __forceinline__ void st(float* p, double a, double b, double c, double d) {
+    *reinterpret_cast<float4*>(p) = make_float4((float)a, (float)b, (float)c, (float)d);
+  }
+};
+
 // ---- mbarrier / bulk-copy PTX (sm_90+; 1-D TMA bulk copy, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t agg_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void agg_mbar_init(uint32_t bar, uint32_t count) {
@@ -458,6 +471,13 @@ __device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uin
                : "memory");
 }
 
+__device__ __forceinline__ void agg_bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void agg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void agg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void agg_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // Masked residual aggregation, v2 (r1 ncu on v0: 1 CTA/SM, DRAM 10 %, latency-bound on the dependent
 // index -> membership -> row loads; fp64 adds predicated instead of branched).
 //   grid (n_groups_total, ceil(K / k_per_cta)); block = 32 (producer warp) + D/4 consumer threads.
@@ -485,8 +505,10 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   const int n_cwarps = (blockDim.x >> 5) - 1;
   const uint32_t row_bytes = (uint32_t)D * 4u;
   float* ring = reinterpret_cast<float*>(agg_smem);
-  float* maskf = reinterpret_cast<float*>(agg_smem + (size_t)kRingRows * row_bytes);   // [row][kSegGroup] 0/1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(maskf + kRingRows * kSegGroup);
+  OutT* staging = reinterpret_cast<OutT*>(agg_smem + (size_t)kRingRows * row_bytes);      // [kSegGroup][D] scaled output
+  float* maskf = reinterpret_cast<float*>(agg_smem + (size_t)kRingRows * row_bytes + (size_t)kSegGroup * D * sizeof(OutT));   // [row][kSegGroup] 0/1
+  unsigned* meta = reinterpret_cast<unsigned*>(maskf + kRingRows * kSegGroup);           // [row] membership word
+  uint64_t* bars = reinterpret_cast<uint64_t*>(meta + kRingRows);
   double* s_red = reinterpret_cast<double*>(bars + 2 * kRingSlots);      // [12 warps][kSegGroup]
   double* s_scale = s_red + 12 * kSegGroup;                              // [kSegGroup]
   const uint32_t bar_full = agg_smem_u32(bars), bar_empty = agg_smem_u32(bars + kRingSlots);
@@ -545,6 +567,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           f0.z = (m_cur & 4u) ? 1.f : 0.f;   f0.w = (m_cur & 8u) ? 1.f : 0.f;
           f1.x = (m_cur & 16u) ? 1.f : 0.f;  f1.y = (m_cur & 32u) ? 1.f : 0.f;
           f1.z = (m_cur & 64u) ? 1.f : 0.f;  f1.w = (m_cur & 128u) ? 1.f : 0.f;
+          meta[rrow] = m_cur;
           *reinterpret_cast<float4*>(maskf + rrow * kSegGroup) = f0;
           *reinterpret_cast<float4*>(maskf + rrow * kSegGroup + 4) = f1;
           agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
@@ -582,29 +605,35 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   // (r1 ncu: the per-(row, segment) branched fp64 adds executed ~128 instructions per row and warp, IPC 1.2.)
   static_assert(kSegGroup == 8, "two float4 mask loads per row");
   double acc[kSegGroup][4];
-  float2 a32[kSegGroup][2];
+  float2 a32[4][2];
 #pragma unroll
-  for (int j = 0; j < kSegGroup; ++j) {
-    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-    a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
-  }
+  for (int j = 0; j < kSegGroup; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
   int since = 0;
   unsigned seq = 0;
   long long t_wait = 0, t_epi = 0, t_e1 = 0, t_e2 = 0, t_e3 = 0;
   const bool probe = dbg != nullptr;
+  // Segments 0-3 of the group go through the fp32 FMA pipe (packed fma.rn.f32x2 with the 0/1 membership as
+  // multiplier, fp32 partial sums, promoted every kFlushEvery rows); segments 4-7 through the fp64 pipe (predicated
+  // DADDs straight into the fp64 accumulators).  The two pipes run concurrently (r1 probe: all eight segments on the
+  // FMA pipe cost ~370 cycles per row -- 3-operand FFMA issues every other cycle per SMSP).
 #define SV_FMA(J, B, RLO, RHI)                                     \
       a32[J][0] = __ffma2_rn(make_float2(B, B), RLO, a32[J][0]);   \
       a32[J][1] = __ffma2_rn(make_float2(B, B), RHI, a32[J][1]);
-#define SV_ROW(R, B0, B1)                                                                   \
+#define SV_DADD(J, M, BIT)                                                                 \
+      if ((M) & (BIT)) { acc[J][0] += rx; acc[J][1] += ry; acc[J][2] += rz; acc[J][3] += rw; }
+#define SV_ROW(R, B0, M)                                                                    \
       {                                                                                     \
         const float2 rlo = make_float2(R.x, R.y), rhi = make_float2(R.z, R.w);              \
         SV_FMA(0, B0.x, rlo, rhi) SV_FMA(1, B0.y, rlo, rhi) SV_FMA(2, B0.z, rlo, rhi) SV_FMA(3, B0.w, rlo, rhi) \
-        SV_FMA(4, B1.x, rlo, rhi) SV_FMA(5, B1.y, rlo, rhi) SV_FMA(6, B1.z, rlo, rhi) SV_FMA(7, B1.w, rlo, rhi) \
+        const double rx = (double)R.x, ry = (double)R.y, rz = (double)R.z, rw = (double)R.w; \
+        SV_DADD(4, M, 16u) SV_DADD(5, M, 32u) SV_DADD(6, M, 64u) SV_DADD(7, M, 128u)        \
       }
 #define SV_FLUSH()                                                                          \
       {                                                                                     \
         since = 0;                                                                          \
-        _Pragma("unroll") for (int j = 0; j < kSegGroup; ++j) {                             \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                     \
           acc[j][0] += (double)a32[j][0].x; acc[j][1] += (double)a32[j][0].y;               \
           acc[j][2] += (double)a32[j][1].x; acc[j][3] += (double)a32[j][1].y;               \
           a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);                                    \
@@ -626,8 +655,8 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       }
       const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)rrow * D + d) : zero4;
       const float4 b0 = *reinterpret_cast<const float4*>(maskf + rrow * kSegGroup);
-      const float4 b1 = *reinterpret_cast<const float4*>(maskf + rrow * kSegGroup + 4);
-      SV_ROW(r, b0, b1)
+      const unsigned mw = meta[rrow];
+      SV_ROW(r, b0, mw)
       if ((seq % kRowsPerSlot) == kRowsPerSlot - 1) {
         __syncwarp();
         if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
@@ -648,6 +677,7 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     }
     long long tp1 = 0;
     if (probe) { tp1 = clock64(); t_e1 += tp1 - te0; }
+    if (tid == 32) agg_bulk_wait_read();   // the previous cluster's staged block has left shared memory
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
     if (cw == 0) {
       // 32 lanes: lane = (quarter q, segment j); each sums the partials of warps q, q+4, q+8, ... in ascending order,
@@ -671,20 +701,32 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
     if (probe) { tp2 = clock64(); t_e2 += tp2 - tp1; }
     asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
     if (probe) t_e3 += clock64() - tp2;
+    // scaled block -> shared-memory staging -> asynchronous bulk stores (TMA): the 8 x D x 8 B of output leave the SM
+    // while the consumers already accumulate the next cluster (r1 probe: direct 16-byte stores cost ~4.6 k cycles per
+    // epilogue at ~21 B/clk/SM and nothing else ran meanwhile)
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
       if (j < ns && act_ch) {
         const double sc = s_scale[j];
-        OutT* o = out + (size_t)(s0 + j) * K * D + (size_t)k * D + d;
-        Store4<OutT>::st(o, acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
+        Stage4<OutT>::st(staging + (size_t)j * D + d, acc[j][0] * sc, acc[j][1] * sc, acc[j][2] * sc, acc[j][3] * sc);
       }
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    }
+    agg_fence_async();
+    asm volatile("bar.sync 1, %0;" ::"r"(n_cwarps * 32) : "memory");
+    if (tid == 32) {
+      const uint32_t blk_bytes = (uint32_t)D * (uint32_t)sizeof(OutT);
+      for (int j = 0; j < ns; ++j)
+        agg_bulk_store(out + (size_t)(s0 + j) * K * D + (size_t)k * D, agg_smem_u32(staging + (size_t)j * D), blk_bytes);
+      agg_bulk_commit();
     }
     if (probe) t_epi += clock64() - te0;
   }
 #undef SV_FLUSH
 #undef SV_ROW
+#undef SV_DADD
 #undef SV_FMA
+  if (tid == 32) agg_bulk_wait_read();   // shared memory must outlive the last asynchronous stores
   if (dbg && tid == 32) {
     unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
     o[4] = (unsigned long long)(clock64() - t_start); o[5] = (unsigned long long)t_wait; o[6] = (unsigned long long)t_epi; o[7] = seq;
@@ -881,7 +923,8 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   int k_per_cta = K;
   while (k_per_cta > 1 && (long long)ng * ((K + k_per_cta - 1) / k_per_cta) < 4 * 148) k_per_cta = (k_per_cta + 1) / 2;
   const dim3 agrid(ng, (K + k_per_cta - 1) / k_per_cta);
-  const size_t asmem = (size_t)kRingRows * D * 4 + kRingRows * kSegGroup * 4 + 2 * kRingSlots * 8 +
+  const size_t asmem = (size_t)kRingRows * D * 4 + (size_t)kSegGroup * D * (out_dtype == SEGVLAD_OUT_F64 ? 8 : 4) +
+                       kRingRows * kSegGroup * 4 + kRingRows * 4 + 2 * kRingSlots * 8 +
                        14 * kSegGroup * 8 + 64;
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   if (out_dtype == SEGVLAD_OUT_F64) {
