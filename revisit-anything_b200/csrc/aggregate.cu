@@ -471,6 +471,11 @@ __device__ __forceinline__ void agg_bulk_load(uint32_t dst, const void* src, uin
                : "memory");
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void agg_bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
 }
@@ -551,15 +556,14 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
       for (int sub = 0; sub < 4; ++sub) {
         const bool mine = (m_cur != 0u) && ((lane >> 3) == sub);
         if (!__any_sync(0xffffffffu, mine)) continue;
-        // converged polling: every lane probes ITS slot's empty barrier without blocking
-        bool ok = !mine;
-        const long long t0 = clock64();
-        for (unsigned spin = 0;; ++spin) {
-          if (!ok) ok = agg_mbar_test(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
-          if (__all_sync(0xffffffffu, ok)) break;
-          if ((spin & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();
-        }
-        const long long t1 = clock64();
+        // Slots are released by the consumers in ring order, so once the slot of the LAST row of this sub-batch is
+        // free every earlier one is too: that one lane blocks in mbarrier.try_wait (the warp sleeps in hardware --
+        // a spinning producer steals issue slots from the consumer warps that share its SM sub-partition, r1 probe).
+        const long long t0 = dbg ? clock64() : 0;
+        const unsigned mm = __ballot_sync(0xffffffffu, mine);
+        if (lane == 31 - __clz(mm)) agg_mbar_wait(bar_empty + 8 * slot, (gen & 1u) ^ 1u);
+        __syncwarp();
+        const long long t1 = dbg ? clock64() : 0;
         if (dbg) t_poll += t1 - t0;
         if (mine) {
           float4 f0, f1;
@@ -567,7 +571,6 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
           f0.z = (m_cur & 4u) ? 1.f : 0.f;   f0.w = (m_cur & 8u) ? 1.f : 0.f;
           f1.x = (m_cur & 16u) ? 1.f : 0.f;  f1.y = (m_cur & 32u) ? 1.f : 0.f;
           f1.z = (m_cur & 64u) ? 1.f : 0.f;  f1.w = (m_cur & 128u) ? 1.f : 0.f;
-          meta[rrow] = m_cur;
           *reinterpret_cast<float4*>(maskf + rrow * kSegGroup) = f0;
           *reinterpret_cast<float4*>(maskf + rrow * kSegGroup + 4) = f1;
           agg_mbar_expect_tx(bar_full + 8 * slot, row_bytes);
@@ -605,73 +608,74 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   // (r1 ncu: the per-(row, segment) branched fp64 adds executed ~128 instructions per row and warp, IPC 1.2.)
   static_assert(kSegGroup == 8, "two float4 mask loads per row");
   double acc[kSegGroup][4];
-  float2 a32[4][2];
+  float2 a32[kSegGroup][2];
 #pragma unroll
-  for (int j = 0; j < kSegGroup; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
+  for (int j = 0; j < kSegGroup; ++j) {
+    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0;
+    a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);
+  }
   int since = 0;
   unsigned seq = 0;
-  long long t_wait = 0, t_epi = 0, t_e1 = 0, t_e2 = 0, t_e3 = 0;
+  long long t_wait = 0, t_epi = 0, t_e1 = 0, t_e2 = 0, t_e3 = 0, t_loop = 0;
   const bool probe = dbg != nullptr;
-  // Segments 0-3 of the group go through the fp32 FMA pipe (packed fma.rn.f32x2 with the 0/1 membership as
-  // multiplier, fp32 partial sums, promoted every kFlushEvery rows); segments 4-7 through the fp64 pipe (predicated
-  // DADDs straight into the fp64 accumulators).  The two pipes run concurrently (r1 probe: all eight segments on the
-  // FMA pipe cost ~370 cycles per row -- 3-operand FFMA issues every other cycle per SMSP).
+  // r1 profile of the row loop: ~65 instructions per row and warp (address arithmetic, generic->shared conversions,
+  // predicate juggling) at SM-level IPC ~2 => issue-bound.  The loop below is kept minimal: explicit shared-space
+  // loads from precomputed 32-bit addresses, 16 packed FMAs, slot hand-shake every kRowsPerSlot rows.
 #define SV_FMA(J, B, RLO, RHI)                                     \
       a32[J][0] = __ffma2_rn(make_float2(B, B), RLO, a32[J][0]);   \
       a32[J][1] = __ffma2_rn(make_float2(B, B), RHI, a32[J][1]);
-#define SV_DADD(J, M, BIT)                                                                 \
-      if ((M) & (BIT)) { acc[J][0] += rx; acc[J][1] += ry; acc[J][2] += rz; acc[J][3] += rw; }
-#define SV_ROW(R, B0, M)                                                                    \
+#define SV_ROW(R, B0, B1)                                                                   \
       {                                                                                     \
         const float2 rlo = make_float2(R.x, R.y), rhi = make_float2(R.z, R.w);              \
         SV_FMA(0, B0.x, rlo, rhi) SV_FMA(1, B0.y, rlo, rhi) SV_FMA(2, B0.z, rlo, rhi) SV_FMA(3, B0.w, rlo, rhi) \
-        const double rx = (double)R.x, ry = (double)R.y, rz = (double)R.z, rw = (double)R.w; \
-        SV_DADD(4, M, 16u) SV_DADD(5, M, 32u) SV_DADD(6, M, 64u) SV_DADD(7, M, 128u)        \
+        SV_FMA(4, B1.x, rlo, rhi) SV_FMA(5, B1.y, rlo, rhi) SV_FMA(6, B1.z, rlo, rhi) SV_FMA(7, B1.w, rlo, rhi) \
       }
 #define SV_FLUSH()                                                                          \
       {                                                                                     \
         since = 0;                                                                          \
-        _Pragma("unroll") for (int j = 0; j < 4; ++j) {                                     \
+        _Pragma("unroll") for (int j = 0; j < kSegGroup; ++j) {                             \
           acc[j][0] += (double)a32[j][0].x; acc[j][1] += (double)a32[j][0].y;               \
           acc[j][2] += (double)a32[j][1].x; acc[j][3] += (double)a32[j][1].y;               \
           a32[j][0] = a32[j][1] = make_float2(0.f, 0.f);                                    \
         }                                                                                   \
       }
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t ring_s = agg_smem_u32(ring) + (act_ch ? d : 0) * 4;   // idle channel quads read (and ignore) quad 0
+  const uint32_t mask_s = agg_smem_u32(maskf);
   for (int k = k0; k < k1; ++k) {
     const int n_rows = grp_cnt[(size_t)g * K + k];
+    long long tl0 = 0;
+    if (probe) tl0 = clock64();
     // rows are consumed in ring order; the full barrier is waited for when a row opens a new slot (every
     // kRowsPerSlot rows) and the empty barrier is signalled when a row closes one
 #pragma unroll 2
     for (int rix = 0; rix < n_rows; ++rix) {
-      const unsigned rrow = seq % kRingRows, slot = rrow / kRowsPerSlot;
-      if ((seq % kRowsPerSlot) == 0) {
+      const unsigned rrow = seq & (kRingRows - 1);
+      if ((seq & (kRowsPerSlot - 1)) == 0) {
         long long tw0 = 0;
         if (probe) tw0 = clock64();
-        agg_mbar_wait(bar_full + 8 * slot, (seq / kRingRows) & 1u);
+        agg_mbar_wait(bar_full + 8 * (rrow / kRowsPerSlot), (seq / kRingRows) & 1u);
         if (probe) t_wait += clock64() - tw0;
       }
-      const float4 r = act_ch ? *reinterpret_cast<const float4*>(ring + (size_t)rrow * D + d) : zero4;
-      const float4 b0 = *reinterpret_cast<const float4*>(maskf + rrow * kSegGroup);
-      const unsigned mw = meta[rrow];
-      SV_ROW(r, b0, mw)
-      if ((seq % kRowsPerSlot) == kRowsPerSlot - 1) {
+      const float4 r = lds128(ring_s + rrow * row_bytes);
+      const float4 b0 = lds128(mask_s + rrow * (kSegGroup * 4));
+      const float4 b1 = lds128(mask_s + rrow * (kSegGroup * 4) + 16);
+      SV_ROW(r, b0, b1)
+      if ((seq & (kRowsPerSlot - 1)) == kRowsPerSlot - 1) {
         __syncwarp();
-        if (lane == 0) agg_mbar_arrive(bar_empty + 8 * slot);
+        if (lane == 0) agg_mbar_arrive(bar_empty + 8 * (rrow / kRowsPerSlot));
       }
       ++seq;
       if (++since >= kFlushEvery) SV_FLUSH()
     }
     // end-of-cluster: promote the remaining partial sums
     long long te0 = 0;
-    if (probe) te0 = clock64();
+    if (probe) { te0 = clock64(); t_loop += te0 - tl0; }
     SV_FLUSH()
     // ---- cluster k complete: intra-norm, row scale, store ----
 #pragma unroll
     for (int j = 0; j < kSegGroup; ++j) {
       double ss = acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1] + acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3];
+      if (!act_ch) ss = 0.0;   // idle channel quads (D % 128 != 0) shadow quad 0: keep them out of the norm
       ss = warp_sum(ss);
       if (lane == 0) s_red[cw * kSegGroup + j] = ss;
     }
@@ -724,13 +728,12 @@ aggregate_kernel(const float* __restrict__ R, const int* __restrict__ cl_ptr, co
   }
 #undef SV_FLUSH
 #undef SV_ROW
-#undef SV_DADD
 #undef SV_FMA
   if (tid == 32) agg_bulk_wait_read();   // shared memory must outlive the last asynchronous stores
   if (dbg && tid == 32) {
     unsigned long long* o = dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16;
     o[4] = (unsigned long long)(clock64() - t_start); o[5] = (unsigned long long)t_wait; o[6] = (unsigned long long)t_epi; o[7] = seq;
-    o[8] = (unsigned long long)t_e1; o[9] = (unsigned long long)t_e2; o[10] = (unsigned long long)t_e3;
+    o[8] = (unsigned long long)t_e1; o[9] = (unsigned long long)t_e2; o[10] = (unsigned long long)t_e3; o[11] = (unsigned long long)t_loop;
   }
 }
 

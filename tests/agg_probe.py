@@ -24,7 +24,7 @@ a = buf.cpu().numpy().reshape(-1, 16)
 a = a[a[:, 0] > 0]
 print("CTAs", len(a))
 names = ["prod_total", "prod_poll", "prod_issue", "prod_slots", "cons_total", "cons_wait", "cons_epi", "cons_slots",
-         "epi_flush+sums", "epi_bar1+norm(w0)", "epi_bar2"]
+         "epi_flush+sums", "epi_bar1+norm(w0)", "epi_bar2", "rowloop(incl wait)"]
 for i, n in enumerate(names):
     print(f"{n:12s} mean {a[:, i].mean():12.0f}  min {a[:, i].min():10d}  max {a[:, i].max():10d}")
 print("cycles/slot (consumer total / slots):", (a[:, 4] / np.maximum(a[:, 7], 1)).mean())
