@@ -152,6 +152,18 @@ int segvlad_vote(const int64_t* matches, const float* sims, int ld, int sims_is_
                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * PCA-whitening projection of segment descriptors (SURVEY 8f "next" row f1).
+ * Replaces func_vpr.py:1419-1443 apply_pca_transform_from_pkl (sklearn PCA.transform, whiten=True; model fitted at
+ * place_rec_pca.py:339-342) and, with normalize_rows != 0, the following func_vpr.py:1673-1676 normalizeFeat.
+ *  X [S, D_in] fp64 (aggregation output), components [D_out, D_in] fp32 (pca.components_), mean [D_in] fp64
+ *  (pca.mean_), explained_variance [D_out] fp32;  Y [S, D_out] fp64 = ((X - mean) @ components^T) / sqrt(ev).
+ */
+size_t segvlad_pca_workspace_bytes(int S, int D_in, int D_out);
+int segvlad_pca_project(const double* X, int S, int D_in, const float* components, const double* mean,
+                        const float* explained_variance, int D_out, int normalize_rows, double* Y,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * NetVLAD + anti-burst aggregation (BASELINE config 5; data parallel over images, no collective).
  * Replaces VLAD-BuFF/models/aggregators/aggregation.py:266-361 NetVLAD.forward (antiburst=True, getWeights
  * :148-162, defaults ab_relu/ab_inv/ab_soft False).

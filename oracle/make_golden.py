@@ -118,6 +118,26 @@ def adjacency_case(ref, name):
     print(name, "ok")
 
 
+def pca_case(ref, name):
+    """Reference apply_pca_transform_from_pkl (func_vpr.py:1419-1443) on a small whitening PCA fitted with sklearn."""
+    import pickle
+    import tempfile
+
+    from sklearn.decomposition import PCA
+    rng = np.random.RandomState(31)
+    train = (rng.randn(300, 96) @ rng.randn(96, 96) * 0.05).astype(np.float32)     # fitted on fp32 like place_rec_pca.py:380
+    pca = PCA(n_components=24, whiten=True, svd_solver="arpack").fit(train)
+    X = rng.randn(11, 96) * 0.05                                                    # fp64 descriptors
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as fh:
+        pickle.dump(pca, fh)
+        path = fh.name
+    Y = ref.apply_pca_transform_from_pkl(torch.from_numpy(X), path).numpy()
+    os.unlink(path)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), X=X, Y=Y, components=pca.components_, mean=pca.mean_,
+                        explained_variance=pca.explained_variance_)
+    print(name, Y.shape, Y.dtype)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
@@ -138,6 +158,7 @@ def main():
     vote_case(ref, "vote_a", n_qimg=6, segs=10, n_rimg=40, rsegs=10, seed=21)
     vote_case(ref, "vote_ties", n_qimg=5, segs=7, n_rimg=12, rsegs=6, seed=22, dup_sims=True)
     adjacency_case(ref, "adjacency")
+    pca_case(ref, "pca_apply")
     # normalizeFeat
     x = np.random.RandomState(5).randn(9, 33)
     np.savez_compressed(os.path.join(OUT, "normalize_feat.npz"), x=x, y=ref.normalizeFeat(x.copy()))

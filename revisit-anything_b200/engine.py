@@ -271,6 +271,27 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
 
 
 # --------------------------------------------------------------------------------------------
+# PCA-whitening projection (row f1)
+# --------------------------------------------------------------------------------------------
+def pca_project(X: torch.Tensor, components: torch.Tensor, mean: torch.Tensor, explained_variance: torch.Tensor,
+                normalize_rows: bool = False) -> torch.Tensor:
+    """Y = ((X - mean) @ components^T) / sqrt(explained_variance) in fp64 (sklearn PCA.transform, whiten=True);
+    optional normalizeFeat.  X [S, D_in] CUDA (any float dtype, computed in fp64), returns [S, D_out] fp64 CUDA."""
+    _need_cuda(X, components, mean, explained_variance)
+    X = X.contiguous().double()
+    S, Din = X.shape
+    W = components.contiguous().float()
+    Dout = W.shape[0]
+    mu = mean.contiguous().double()
+    ev = explained_variance.contiguous().float()
+    Y = torch.empty((S, Dout), dtype=torch.float64, device=X.device)
+    ws = _ws(lib().segvlad_pca_workspace_bytes(S, Din, Dout), X.device)
+    check(lib().segvlad_pca_project(_ptr(X), S, Din, _ptr(W), _ptr(mu), _ptr(ev), Dout, int(normalize_rows), _ptr(Y),
+                                    _ptr(ws), ws.numel(), _stream()), "segvlad_pca_project")
+    return Y
+
+
+# --------------------------------------------------------------------------------------------
 # NetVLAD + anti-burst (config 5)
 # --------------------------------------------------------------------------------------------
 def netvlad_antiburst(x: torch.Tensor, centroids: torch.Tensor, conv_weight: torch.Tensor,

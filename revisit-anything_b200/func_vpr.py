@@ -8,6 +8,7 @@ calling
     seg_vlad_gpu_single / seg_vlad_gpu_single_img   (func_vpr.py:1065-1138)
     vlad_single / vlad_matmuls_per_cluster          (func_vpr.py:1140-1210)
     get_matches / weighted_borda_count              (func_vpr.py:61-243)
+    apply_pca_transform_from_pkl                    (func_vpr.py:1419-1443)
     calc_recall, normalizeFeat, nbrMasksAGGFastSingle, getIdxSingleFast, preload_masks,
     first_k_unique_indices                          (host-side helpers, kept on the host as in the reference)
 
@@ -95,6 +96,39 @@ def vlad_matmuls_per_cluster(num_c, masks, res, clus_labels, adjMat=None, device
     out = engine.aggregate_residuals(res.float(), clus_labels.to(dev), N, D, int(num_c), bits, [masks.shape[0]], adj,
                                      out_dtype=torch.float64)
     return out, time.time() - t0
+
+
+# ------------------------------------------------------------------------------------------------
+# PCA-whitening apply  (func_vpr.py:1419-1443)
+# ------------------------------------------------------------------------------------------------
+_PCA_CACHE = {}
+
+
+def _load_pca(pca_model_path):
+    """The reference un-pickles the ~200 MB sklearn model on EVERY batch (func_vpr.py:1434-1435); here the three arrays
+    the transform needs stay resident on the GPU, keyed by (path, mtime)."""
+    import os
+    import pickle
+    key = (pca_model_path, os.path.getmtime(pca_model_path))
+    if key not in _PCA_CACHE:
+        with open(pca_model_path, "rb") as fh:
+            pca = pickle.load(fh)
+        if not getattr(pca, "whiten", False):
+            raise ValueError("segvlad: the SegVLAD PCA model is fitted with whiten=True (place_rec_pca.py:339)")
+        dev = _dev()
+        _PCA_CACHE.clear()
+        _PCA_CACHE[key] = (torch.from_numpy(np.ascontiguousarray(pca.components_)).to(dev),
+                           torch.from_numpy(np.asarray(pca.mean_, dtype=np.float64)).to(dev),
+                           torch.from_numpy(np.ascontiguousarray(pca.explained_variance_)).to(dev))
+    return _PCA_CACHE[key]
+
+
+def apply_pca_transform_from_pkl(data_tensor, pca_model_path, device_out=False):
+    """func_vpr.py:1419-1443: sklearn PCA.transform (whiten) of a [B_seg, 49152] descriptor batch; returns a CPU tensor
+    like the reference (or the CUDA tensor with device_out=True)."""
+    comp, mean, ev = _load_pca(pca_model_path)
+    y = engine.pca_project(data_tensor.to(_dev()), comp, mean, ev, normalize_rows=False)
+    return y if device_out else y.cpu()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -105,3 +105,12 @@ def test_superseg_membership_and_empty_cluster():
     assert float(out[3].abs().max()) == 0.0
     nrm = out[:3].norm(dim=1)
     np.testing.assert_allclose(nrm.numpy(), 1.0, atol=1e-12)
+
+
+def test_pca_apply_matches_reference(golden_dir):
+    g = _load(golden_dir, "pca_apply")
+    y = O.pca_apply(g["X"], g["mean"], g["components"], g["explained_variance"])
+    # The golden vector comes from the reference function run with the sklearn installed HERE (1.9): it evaluates
+    # X @ W^T - (mean @ W^T) with the bias in fp32 (mean_/components_ are fp32), ~1e-8 absolute.  The oracle follows the
+    # reference's PINNED sklearn 1.3.2 (segvlad.yaml:75): (X - mean) @ W^T in fp64.  1e-5 relative is the path tolerance.
+    np.testing.assert_allclose(y, g["Y"], rtol=2e-5, atol=5e-8)
