@@ -67,7 +67,7 @@ pca_finalize_kernel(const double* __restrict__ part, int n_split, const float* _
   for (int o = threadIdx.x; o < Dout; o += 256) {
     double v = 0.0;
     for (int z = 0; z < n_split; ++z) v += part[((size_t)z * S + s) * Dout + o];
-    v /= sqrt((double)ev[o]);
+    v /= (double)sqrtf(ev[o]);   // sklearn: np.sqrt(explained_variance_) is evaluated in the array's fp32, then divides fp64
     Y[(size_t)s * Dout + o] = v;
     ss += v * v;
   }

@@ -81,12 +81,16 @@ def recall_segloc(workdir, dataset_name, experiment_config, experiment_name, seg
 
 def build_segment_descriptors(tokens: Sequence[torch.Tensor], masks: Sequence[Sequence[np.ndarray]],
                               c_centers: torch.Tensor, cfg: dict, order: int, desc_dim: int = 1536,
-                              batch_images: int = 32, out_dtype=torch.float64, adjacency: Optional[Sequence] = None):
+                              batch_images: int = 32, out_dtype=torch.float64, adjacency: Optional[Sequence] = None,
+                              pca_model_path: Optional[str] = None):
     """Batched equivalent of the per-image loop place_rec_main.py:244-281 (reference side) / :309-352 (query
     side): for every image, SuperSegment adjacency on the host (scipy, as in the reference), then ONE batched
     aggregation launch per `batch_images` images; descriptors stay on the GPU.
     tokens[i]: [1,D,dh,dw] fp32 (CPU or CUDA); masks[i]: list of [Hm,Wm] bool.
-    Returns (segFtVLAD [S_total, K*D] CUDA, imInds [S_total] int64 numpy)."""
+    With `pca_model_path` (experiment_config['pca'], place_rec_main.py:261-272) every batch is projected on the device
+    with the whitening PCA (func_vpr.apply_pca_transform_from_pkl semantics) before it is kept, so the [S, K*D] fp64
+    block never leaves the GPU and only [S, n_components] rows accumulate.
+    Returns (segFtVLAD [S_total, K*D or n_components] CUDA, imInds [S_total] int64 numpy)."""
     dev = _dev()
     H, W = cfg["desired_height"], cfg["desired_width"]
     N = (H // 14) * (W // 14)
@@ -107,5 +111,7 @@ def build_segment_descriptors(tokens: Sequence[torch.Tensor], masks: Sequence[Se
             im_inds.append(np.full(len(masks[i]), i, dtype=np.int64))
         gd = engine.aggregate_batch(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
                                     adjs if order else None, out_dtype=out_dtype)
+        if pca_model_path is not None:
+            gd = func_vpr.apply_pca_transform_from_pkl(gd, pca_model_path, device_out=True)
         outs.append(gd)
     return torch.cat(outs), np.concatenate(im_inds)
