@@ -399,22 +399,6 @@ __global__ void nonempty_kernel(const uint32_t* __restrict__ sup, const int* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-template <typename OutT> struct Store4;
-template <> struct Store4<double> {
-  static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
-    __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
-    __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(c, d));
-  }
-};
-template <> struct Store4<float> {
-  static __device__ __forceinline__ void st(float* p, double a, double b, double c, double d) {
-    __stcs(reinterpret_cast<float4*>(p), make_float4((float)a, (float)b, (float)c, (float)d));
-  }
-};
-
-// optional timing probe (tests/agg_probe.py): per-CTA cycle counters written by the producer / first consumer warp
-static unsigned long long* g_agg_dbg = nullptr;
-
 template <typename OutT> struct Stage4;
 template <> struct Stage4<double> {
   static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
