@@ -399,6 +399,9 @@ __global__ void nonempty_kernel(const uint32_t* __restrict__ sup, const int* __r
 }
 
 // ------------------------------------------------------------------------------------------------
+// optional timing probe (tests/agg_probe.py): per-CTA cycle counters written by the producer / first consumer warp
+static unsigned long long* g_agg_dbg = nullptr;
+
 template <typename OutT> struct Stage4;
 template <> struct Stage4<double> {
   static __device__ __forceinline__ void st(double* p, double a, double b, double c, double d) {
