@@ -1,0 +1,59 @@
+"""Full-size properties of the matching path (sizes the CPU oracle cannot finish in seconds): multi-block query sets,
+large banks, size-independent invariants + brute-force fp64 check on a sample of rows (torch on the GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from gpu_util import assert_knn_close
+from revisit_anything_b200 import engine, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _brute_fp64(q, r, k):
+    d = (q.double() ** 2).sum(1)[:, None] + (r.double() ** 2).sum(1)[None, :] - 2.0 * (q.double() @ r.double().T)
+    d.clamp_(min=0)
+    v, i = torch.sort(d, dim=1, stable=True)
+    return v[:, :k].cpu().numpy(), i[:, :k].cpu().numpy()
+
+
+def test_config4_slice_two_query_blocks_and_shards():
+    # 20k queries (2 query blocks of the workspace) x 300k refs x 512-D (config-4 descriptor size), k = 200
+    Nq, Nr, D, k = 20000, 300000, 512, 200
+    q, r = synth.make_descriptor_bank(Nq, Nr, D, seed=44, planted=2000, device=DEV)
+    qb, rb = engine.Bank.prepare(q), engine.Bank.prepare(r)
+    d2, idx = engine.knn(qb, rb, k)
+    torch.cuda.synchronize()
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all()), "distances must be ascending"
+    assert int(idx.min()) >= 0 and int(idx.max()) < Nr
+    srt = torch.sort(idx, dim=1).values
+    assert bool((srt[:, 1:] != srt[:, :-1]).all()), "a reference row may appear once per query"
+    # returned distances are the exact fp32 distances of the returned rows (sample of rows, fp64 recomputation)
+    rows = torch.randperm(Nq, device=DEV)[:256]
+    diff = q[rows].double()[:, None, :] - r[idx[rows]].double()
+    np.testing.assert_allclose(d2[rows].cpu().numpy(), (diff * diff).sum(-1).cpu().numpy(), rtol=1e-5, atol=2e-6)
+    # completeness on a sample: brute force over the whole bank in fp64
+    sample = torch.cat([rows[:48], torch.tensor([0, 16383, 16384, Nq - 1], device=DEV)])   # incl. block boundaries
+    d64, i64 = _brute_fp64(q[sample], r, k + 8)
+    assert_knn_close(d2[sample].cpu().numpy(), idx[sample].cpu().numpy(), d64, i64, k_check=k)
+    # row-sharded search + merge == single search (bit-identical)
+    bounds = [0, 90000, 200000, Nr]
+    pd, pi = [], []
+    for g in range(3):
+        a, b = engine.knn(qb, engine.Bank.prepare(r[bounds[g]:bounds[g + 1]]), k, row_offset=bounds[g])
+        pd.append(a)
+        pi.append(b)
+    md, mi = engine.merge_topk(torch.stack(pd), torch.stack(pi))
+    assert torch.equal(md, d2) and torch.equal(mi, idx)
+
+
+def test_single_cta_variant_agrees(monkeypatch):
+    # cta_group::1 and cta_group::2 kernels feed the same exact re-score: identical outputs
+    q, r = synth.make_descriptor_bank(3000, 50000, 1536, seed=45, planted=300, device=DEV)
+    qb, rb = engine.Bank.prepare(q), engine.Bank.prepare(r)
+    d2a, ia = engine.knn(qb, rb, 200)
+    monkeypatch.setenv("SEGVLAD_KNN_CTAS", "1")
+    d2b, ib = engine.knn(qb, rb, 200)
+    torch.cuda.synchronize()
+    assert torch.equal(d2a, d2b) and torch.equal(ia, ib)
