@@ -35,6 +35,12 @@ SEGS_PER_IMG = 100
 CPU_SAMPLE_Q = 2000          # bounded CPU sample: 2000 query segs (20 query images) x the full 100k-row bank
 
 
+def _traffic():
+    """DRAM traffic of the dominant kernels from the committed `ncu --set full` capture (profiles/r1_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -229,7 +235,8 @@ def aggregation_side_bench(device, peaks):
             "algorithmic_bytes_per_image": bytes_img,
             "roofline": {"bound": "hbm", "achieved": B * bytes_img / (kern_ms * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": B * bytes_img / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None}}
+                         "frac": B * bytes_img / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "traffic": _traffic().get("aggregate_dram_bytes_per_launch")}}
 
 
 def main():
@@ -350,7 +357,10 @@ def main():
                 "d2h_bytes_per_step": int(preds_host.numel() * 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "knn_tc_filter_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved / peak,
+                     "traffic": _traffic().get("knn_tc_filter_dram_bytes_per_step"),
+                     "traffic_note": "dram read+write bytes of the kernel's launches in one step (ncu --set full, "
+                                     "profiles/r1_ncu_knn_tc_filter_final.txt); algorithmic bytes (Nq+Nr)*D*4 = 0.68 GB",
                      "note": "algorithmic 2*D FLOP/pair; the kernel issues 3 bf16 MMA passes (hi.hi+hi.mid+mid.hi), "
                              "so tensor-pipe utilisation is 3x this fraction; peak = sustained cuBLAS bf16",
                      "kernel_ms_per_step": tc_ms_step, "launches_per_step": tc_launches / args.steps,
