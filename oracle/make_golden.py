@@ -138,9 +138,55 @@ def pca_case(ref, name):
     print(name, Y.shape, Y.dtype)
 
 
+def anyloc_case(ref):
+    """Reference utilities.VLAD.generate (hard assignment, whole image) and func_vpr.get_recall / calculate_map.
+    fast_pytorch_kmeans is absent offline: VLAD.kmeans is a stub applying the library's published cosine rule."""
+    import sys
+
+    import torch
+    util = sys.modules["utilities"]
+
+    class _Predict:
+        def __init__(self, c):
+            self.centroids = c
+
+        def predict(self, x):
+            a = x / (x.norm(dim=-1, keepdim=True) + 1e-8)
+            b = self.centroids / (self.centroids.norm(dim=-1, keepdim=True) + 1e-8)
+            return (a @ b.t()).max(dim=-1)[1]
+
+    g = torch.Generator().manual_seed(41)
+    K, D, N, B = 8, 64, 300, 5
+    centers = 0.5 * torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1)
+    centers[5] = 3.0 * centers[5]          # a far centre that attracts few tokens; cluster 7 made empty below
+    tokens = torch.randn(B, N, D, generator=g) + 2.0 * centers[torch.randint(0, K - 1, (B, N), generator=g)]
+    vlad = util.VLAD(K, desc_dim=None, dist_mode="cosine", vlad_mode="hard", cache_dir=None)
+    vlad.c_centers, vlad.kmeans, vlad.desc_dim = centers, _Predict(centers), D
+    out = torch.stack([vlad.generate(tokens[b]) for b in range(B)])
+    np.savez_compressed(os.path.join(OUT, "anyloc_vlad.npz"), tokens=tokens.numpy(), centers=centers.numpy(),
+                        vlad=out.numpy())
+    print("anyloc_vlad", out.shape, out.dtype)
+
+    rng = np.random.RandomState(43)
+    n_db, n_q, Dg, k = 60, 25, 48, 5
+    db = ref.normalizeFeat(rng.randn(n_db, Dg).astype(np.float32))
+    q = ref.normalizeFeat((db[rng.randint(0, n_db, n_q)] + 0.6 * rng.randn(n_q, Dg)).astype(np.float32))
+    gt = [list(range(max(0, i * 2 - 2), min(n_db, i * 2 + 3))) for i in range(n_q)]
+    gt[3] = []
+    recall, per_query, matches = ref.get_recall(db, q, gt, analysis=True, k=k)
+    nbrs = np.stack([m["img_id_r"] for m in matches])
+    qr = ref.convert_to_queries_results_for_map([list(r) for r in nbrs], gt)
+    np.savez_compressed(os.path.join(OUT, "anyloc_recall.npz"), db=db, q=q, k=k,
+                        gt=np.array([np.array(x + [-1] * (8 - len(x))) for x in gt]), recall=np.asarray(recall),
+                        per_query=np.asarray(per_query), nbrs=nbrs, map=ref.calculate_map(qr),
+                        ap=np.array([ref.calculate_ap(r) for r in qr], dtype=np.float64))
+    print("anyloc_recall", recall)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_shim.load()
+    anyloc_case(ref)
     seg_vlad_img, _ = _cpu_patched(ref)
     torch.manual_seed(17)
     np.random.seed(17)

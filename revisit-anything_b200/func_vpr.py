@@ -11,6 +11,8 @@ calling
     apply_pca_transform_from_pkl                    (func_vpr.py:1419-1443)
     calc_recall, normalizeFeat, nbrMasksAGGFastSingle, getIdxSingleFast, preload_masks,
     first_k_unique_indices                          (host-side helpers, kept on the host as in the reference)
+    aggFt(..., 'vlad'), get_recall, calculate_ap / calculate_map / convert_to_queries_results_for_map
+                                                    (AnyLoc whole-image baseline, func_vpr.py:352-392, 833-956)
 
 Batched, device-resident fast paths (no per-image D2H) live in `engine.py` / `place_rec_main.py`.
 """
@@ -279,3 +281,87 @@ def normalizeFeat(rfts):
     rfts = np.array(rfts).reshape([len(rfts), -1])
     rfts /= np.linalg.norm(rfts, axis=1)[:, None]
     return rfts
+
+
+# ------------------------------------------------------------------------------------------------
+# AnyLoc whole-image baseline (place_rec_main.py:379-409): aggFt 'vlad', get_recall, mAP helpers
+# ------------------------------------------------------------------------------------------------
+def _open_store(desc_path):
+    """A path is opened with h5py when that package exists; any mapping {key: {'ift_dino': array}} is used as is."""
+    if isinstance(desc_path, (str, bytes)):
+        try:
+            import h5py
+        except ImportError as e:
+            raise RuntimeError("segvlad: h5py is not installed; pass an opened mapping {img: {'ift_dino': array}} or "
+                               "convert the file with revisit_anything_b200.store") from e
+        return h5py.File(desc_path, "r")
+    return desc_path
+
+
+def aggFt(desc_path, masks, segRange, cfg, aggType, vlad=None, upsample=False, segment_global=False, segment=False,
+          batch_images=64):
+    """func_vpr.py:886-956 for the branch the drivers use: aggType='vlad', whole image (segment=False): every image's
+    tokens [1,D,dh,dw] -> [N,D] -> channel L2-norm -> VLAD (our `utilities.VLAD.generate_multi`, batched on the GPU).
+    Returns a list of fp32 numpy [K*D] vectors in natural key order, like the reference."""
+    if aggType != "vlad" or segment or segment_global:
+        raise NotImplementedError("aggFt: only aggType='vlad' on whole images is on the AnyLoc baseline path "
+                                  "(place_rec_main.py:383-384)")
+    if vlad is None:
+        raise ValueError("aggFt: a fitted VLAD object is required for aggType='vlad'")
+    f = _open_store(desc_path)
+    keys = sorted(f.keys(), key=_natural_key)
+    out = []
+    for b0 in range(0, len(keys), batch_images):
+        toks = []
+        for kname in keys[b0:b0 + batch_images]:
+            a = np.asarray(f[kname]["ift_dino"][()])
+            toks.append(torch.from_numpy(np.ascontiguousarray(a.reshape(a.shape[1], -1).T)))   # [N, D]
+        for gd in vlad.generate_multi(toks):
+            out.append(gd.numpy())
+    return out
+
+
+def get_recall(database_vectors, query_vectors, gt, analysis=False, k=5):
+    """func_vpr.py:833-883.  The reference asks a sklearn KDTree for the k nearest database rows of each query (exact
+    Euclidean); here the exhaustive search kernel of the SegVLAD path does it.  Returns (recall in percent [k],
+    matches) or (recall, recall_per_query, matches) with analysis=True; `matches[i]['img_id_r']` holds the k ids."""
+    dev = _dev()
+    db = torch.as_tensor(np.asarray(database_vectors), dtype=torch.float32).to(dev)
+    q = torch.as_tensor(np.asarray(query_vectors), dtype=torch.float32).to(dev)
+    kk = min(int(k), db.shape[0])
+    _, idx = engine.knn(engine.Bank.prepare(q), engine.Bank.prepare(db), kk)
+    idx = idx.cpu().numpy()
+    recall = [0] * k
+    per_query = [0] * len(idx)
+    matches = []
+    n_eval = 0
+    for i in range(len(idx)):
+        matches.append({"seg_id_q": -1, "img_id_r": idx[i], "seg_id_r": -1, "img_id_to_seg_id": -1})
+        if len(gt[i]) == 0:
+            continue
+        n_eval += 1
+        for j in range(idx.shape[1]):
+            if idx[i][j] in gt[i]:
+                recall[j] += 1
+                per_query[i] = 1
+                break
+    recall = (np.cumsum(recall) / float(n_eval)) * 100
+    return (recall, per_query, matches) if analysis else (recall, matches)
+
+
+def convert_to_queries_results_for_map(max_seg_preds, gt):
+    return [[ref in gt[qi] for ref in refs] for qi, refs in enumerate(max_seg_preds)]
+
+
+def calculate_ap(retrieved_items):
+    hits, acc = 0, 0.0
+    for rank, rel in enumerate(retrieved_items, start=1):
+        if rel:
+            hits += 1
+            acc += hits / rank
+    return acc / hits if hits else 0
+
+
+def calculate_map(queries_results):
+    aps = [calculate_ap(r) for r in queries_results]
+    return sum(aps) / len(aps) if aps else 0

@@ -74,7 +74,8 @@ def recall_segloc(workdir, dataset_name, experiment_config, experiment_name, seg
     max_seg_recalls = func_vpr.calc_recall(max_seg_preds, gt, N_PRED)
     print("VLAD + PCA Results \n ")
     if map_calculate:
-        print("mAP calculation is outside the SegVLAD hot path (func_vpr.calculate_map): skipped")
+        queries_results = func_vpr.convert_to_queries_results_for_map(max_seg_preds, gt)
+        print(f"Mean Average Precision (mAP): {func_vpr.calculate_map(queries_results)}")
     print("Max Seg Logs: ", max_seg_recalls)
     return max_seg_recalls
 
@@ -115,3 +116,14 @@ def build_segment_descriptors(tokens: Sequence[torch.Tensor], masks: Sequence[Se
             gd = func_vpr.apply_pca_transform_from_pkl(gd, pca_model_path, device_out=True)
         outs.append(gd)
     return torch.cat(outs), np.concatenate(im_inds)
+
+
+def recall_anyloc(dino_r_path, dino_q_path, cfg, vlad, gt, topk_value=5):
+    """AnyLoc-VLAD-DINOv2 baseline branch, place_rec_main.py:379-391: whole-image VLAD of every reference / query image
+    (`func_vpr.aggFt(..., 'vlad')`), normalizeFeat, Recall@1..topk through `func_vpr.get_recall`.
+    `dino_*_path`: HDF5 path (needs h5py) or any mapping with the same indexing (store.DirStore).
+    Returns (recall in percent, match_info, imFts1_vlad, imFts2_vlad)."""
+    im1 = func_vpr.aggFt(dino_r_path, None, None, cfg, "vlad", vlad, upsample=True)
+    im2 = func_vpr.aggFt(dino_q_path, None, None, cfg, "vlad", vlad, upsample=True)
+    recall, match_info = func_vpr.get_recall(func_vpr.normalizeFeat(im1), func_vpr.normalizeFeat(im2), gt, k=topk_value)
+    return recall, match_info, im1, im2

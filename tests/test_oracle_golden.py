@@ -114,3 +114,30 @@ def test_pca_apply_matches_reference(golden_dir):
     # X @ W^T - (mean @ W^T) with the bias in fp32 (mean_/components_ are fp32), ~1e-8 absolute.  The oracle follows the
     # reference's PINNED sklearn 1.3.2 (segvlad.yaml:75): (X - mean) @ W^T in fp64.  1e-5 relative is the path tolerance.
     np.testing.assert_allclose(y, g["Y"], rtol=2e-5, atol=5e-8)
+
+
+def test_anyloc_vlad_matches_reference(golden_dir):
+    """f4: utilities.VLAD.generate (whole-image hard-assignment VLAD, fp32)."""
+    g = _load(golden_dir, "anyloc_vlad")
+    c = torch.from_numpy(g["centers"])
+    for b in range(g["tokens"].shape[0]):
+        out = O.anyloc_vlad_generate(torch.from_numpy(g["tokens"][b]), c).numpy()
+        np.testing.assert_allclose(out, g["vlad"][b], rtol=0, atol=2e-7)
+    # same quantity through the SegVLAD formulation (one all-ones segment, fp64): the fp32 reference sits within 1e-5
+    x = torch.nn.functional.normalize(torch.from_numpy(g["tokens"][0]), dim=1)
+    seg, _, _ = O.vlad_single(x, c, torch.ones(1, x.shape[0], dtype=torch.bool), None)
+    np.testing.assert_allclose(seg[0].numpy(), g["vlad"][0], rtol=1e-5, atol=1e-6)
+
+
+def test_anyloc_recall_and_map_match_reference(golden_dir):
+    """f4: func_vpr.get_recall (KD-tree == exact neighbours), calculate_ap / calculate_map."""
+    g = _load(golden_dir, "anyloc_recall")
+    gt = [[int(v) for v in row if v >= 0] for row in g["gt"]]
+    recall, per_query, nbrs = O.get_recall(g["db"], g["q"], gt, k=int(g["k"]))
+    np.testing.assert_array_equal(nbrs, g["nbrs"])
+    np.testing.assert_allclose(recall, g["recall"], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(per_query, g["per_query"])
+    qr = O.results_for_map([list(r) for r in nbrs], gt)
+    np.testing.assert_allclose([O.calculate_ap(r) for r in qr], g["ap"], rtol=0, atol=1e-15)
+    assert abs(O.calculate_map(qr) - float(g["map"])) < 1e-15
+    assert O.calculate_map([]) == 0 and O.calculate_ap([False, False]) == 0
