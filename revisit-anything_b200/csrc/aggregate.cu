@@ -19,6 +19,7 @@
 // streaming stores.  Accumulation is fp64 like the reference (the addends are fp32 values, so the sums
 // are exact to ~1e-16 and independent of the summation order in practice).
 #include "common.cuh"
+#include "aggregate_tc.cuh"
 
 namespace segvlad {
 
@@ -780,6 +781,7 @@ __global__ void mask_to_membership_kernel(const uint8_t* __restrict__ masks, int
 struct AggLayout {
   float* chatT; float* R; float* part; float* ssq; float* nrm; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT; int* gcnt;
   int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
+  __nv_bfloat16* RT; int* tile_tbl;   // tensor-core path (aggregate_tc.cu)
   size_t total;
 };
 
@@ -806,6 +808,8 @@ static AggLayout carve_agg(void* ws, int B, int N, int D, int K, int S_total) {
   L.grp_img = c.take<int>(max_groups);
   L.grp_seg0 = c.take<int>(max_groups);
   L.grp_nseg = c.take<int>(max_groups);
+  L.RT = c.take<__nv_bfloat16>(agg_tc_supported(N, D, K) ? agg_tc_rt_elems(B, N, D) : 0);
+  L.tile_tbl = c.take<int>((size_t)4 * agg_tc_max_tiles(B, S_total));
   L.total = c.total();
   return L;
 }
@@ -826,7 +830,8 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
                             const int32_t* seg_offsets_host, const uint8_t* adj, void* out, int out_dtype,
                             int32_t* labels_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   SV_REQUIRE(B > 0 && N > 0 && D > 0 && K > 0, "aggregate: non-positive shape");
-  SV_REQUIRE(D % 128 == 0 ? D <= 1536 : (D % 4 == 0 && D <= 1536), "aggregate: D_t must be a multiple of 4 and <= 1536 (got %d)", D);
+  const bool use_tc = agg_tc_supported(N, D, K);
+  SV_REQUIRE(use_tc || (D % 4 == 0 && D <= 1536), "aggregate: D_t must be a multiple of 4 and <= 1536 (got %d)", D);
   SV_REQUIRE(K <= 128, "aggregate: K must be <= 128 (got %d)", K);
   const int layout = token_layout & 1, prenorm = (token_layout & SEGVLAD_TOKENS_PRENORMALIZED) ? 1 : 0;
   SV_REQUIRE((token_layout & ~3) == 0, "aggregate: bad token_layout");
@@ -907,6 +912,23 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   SV_CHECK_LAUNCH();
   nonempty_kernel<<<S_total, 32, 0, st>>>(sup, labels, L.seg_off, B, N, W, L.cpred);
   SV_CHECK_LAUNCH();
+  if (use_tc) {
+    // tensor-core path: mask tile x bf16-split residual planes per (image, 128-segment tile, cluster)
+    AggTcArgs ta;
+    ta.R = R; ta.cl_ptr = L.cl_ptr; ta.cl_tok = L.cl_tok; ta.memS = L.memT; ta.cpred = L.cpred; ta.norms = L.norms;
+    ta.seg_offsets_host = seg_offsets_host; ta.B = B; ta.N = N; ta.D = D; ta.K = K; ta.S_total = S_total;
+    ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl;
+    const int rc = agg_tc_run(ta, st);
+    if (rc != SEGVLAD_OK) return rc;
+    if (out_dtype == SEGVLAD_OUT_F64)
+      rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
+    else
+      rownorm_fixup_kernel<float><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (float*)out);
+    SV_CHECK_LAUNCH();
+    if (labels_out && !residuals_in)
+      SV_CHECK_CUDA(cudaMemcpyAsync(labels_out, L.labels, sizeof(int) * (size_t)B * N, cudaMemcpyDeviceToDevice, st));
+    return SEGVLAD_OK;
+  }
   // one warp of producers + D/4 consumer threads; clusters are split over blockIdx.y until the grid has
   // >= ~2 CTAs per SM (single-image calls) -- batched calls keep every cluster of a group in one CTA
   const int threads = 32 + (int)align_up((size_t)(D / 4), 32);

@@ -1,0 +1,443 @@
+// Masked residual aggregation on the 5th-generation tensor cores (sm_100a) -- SURVEY 8 rows a2/a3.
+//
+// Replaces the per-cluster `M'.double() @ res[inds]` + intra-normalisation + row normalisation of
+// vlad_matmuls_per_cluster (func_vpr.py:1191-1205).  For one image and one cluster k the block of all segments is a
+// small dense contraction
+//       V_k [S x D] = M_k [S x n_k] . R_k [n_k x D]        M = 0/1 SuperSegment membership, R = fp32 residual rows
+// with n_k ~ N/K tokens.  The SIMT kernel (aggregate.cu) evaluates it as dense masked FMAs for 8 segments per CTA and
+// therefore re-reads every residual row S/8 times and is bound by the FMA pipe and its serial epilogue (r1 profile:
+// 32 % of the HBM write roofline).  Here the contraction runs on tcgen05:
+//   * R is split once into three bf16 planes (hi + mid + lo = all 24 fp32 mantissa bits; the 0/1 mask is exact in bf16,
+//     so every product is exact) stored TRANSPOSED and label-sorted, RT[plane][image][d][i]: the tokens of a cluster
+//     are then a contiguous K-major column range that TMA tiles straight into the SWIZZLE_128B operand layout;
+//   * one CTA owns (image, tile of 128 segments, cluster): A = mask tile [128 x 64 tokens] written into shared memory
+//     by two builder warps from the membership words, B = [128 channels x 64 tokens] x 3 planes by TMA, D = fp32
+//     accumulators in TMEM (4 buffers of 128 columns);
+//   * the block norm needs all D channels but TMEM holds 512 of them, so the contraction is issued twice -- a norm
+//     sweep (TMEM -> sum of squares, no stores) and a write sweep (TMEM -> x scale -> fp64 -> shared staging -> bulk
+//     stores).  The tensor work is ~10 % of the write time, the operand re-read comes from L2;
+//   * thread = segment row (TMEM lane), so norms and scales never leave the thread: no reductions, no CTA barriers.
+// Accumulation is fp32 in TMEM (truncating adds, measured ~4e-8 relative per MMA): <= 3 * n_k / 16 MMAs per element,
+// i.e. ~1e-6 relative for the largest clusters -- inside the 1e-5 descriptor tolerance; the planes are accumulated
+// small-to-large.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-5 epilogue, 6-7 mask-tile builders.
+#include "aggregate_tc.cuh"
+
+#include <stdlib.h>
+
+#include "tc_ptx.cuh"
+
+namespace segvlad {
+
+constexpr int kTcThreadsAgg = 256;
+constexpr int kTcStages = 2;
+constexpr uint32_t kTcTileBytes = kTcSegTile * kTcTokChunk * 2;          // 16 KB: one [128 x 64] bf16 operand tile
+constexpr uint32_t kTcStageBytes = 4 * kTcTileBytes;                     // A + 3 B planes
+constexpr int kTcBufs = 512 / kTcPassN;                                  // TMEM accumulator buffers
+constexpr double kEpsTc = 1e-12;
+
+template <typename OutT> struct StageRow;   // bytes of one staged row piece (32 values) + 16 B pad (bank spread)
+template <> struct StageRow<double> { static constexpr uint32_t kBytes = 32 * 8 + 16; };
+template <> struct StageRow<float> { static constexpr uint32_t kBytes = 32 * 4 + 16; };
+
+template <typename OutT> __host__ __device__ constexpr size_t agg_tc_smem() {
+  return 1024 + (size_t)kTcStages * kTcStageBytes + (size_t)4 * 2 * 32 * StageRow<OutT>::kBytes + 256;
+}
+
+// ------------------------------------------------------------------------------------------------
+// R [B][N][D] fp32 -> RT [3][B][D][Np] bf16 (lo, mid, hi), columns in label-sorted order, zero padded to Np.
+__global__ void __launch_bounds__(256)
+rt_planes_kernel(const float* __restrict__ R, const int* __restrict__ cl_tok, int B, int N, int D, int Np,
+                 __nv_bfloat16* __restrict__ RT) {
+  __shared__ float tile[32][65];
+  const int i0 = blockIdx.x * 64, d0 = blockIdx.y * 32, b = blockIdx.z;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int t = w * 8 + r, i = i0 + t;
+    float v = 0.f;
+    if (i < N && d0 + lane < D) {
+      const int n = cl_tok[(size_t)b * N + i];
+      v = R[((size_t)b * N + n) * D + d0 + lane];
+    }
+    tile[lane][t] = v;
+  }
+  __syncthreads();
+  const size_t plane = (size_t)B * D * Np;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int dd = w * 4 + rr, d = d0 + dd;
+    if (d >= D) continue;
+    const float x0 = tile[dd][2 * lane], x1 = tile[dd][2 * lane + 1];
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    const float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
+    const __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(r0 - __bfloat162float(m0)), l1 = __float2bfloat16_rn(r1 - __bfloat162float(m1));
+    const size_t o = ((size_t)b * D + d) * Np + i0 + 2 * lane;
+    *reinterpret_cast<__nv_bfloat162*>(RT + o) = __halves2bfloat162(l0, l1);
+    *reinterpret_cast<__nv_bfloat162*>(RT + plane + o) = __halves2bfloat162(m0, m1);
+    *reinterpret_cast<__nv_bfloat162*>(RT + 2 * plane + o) = __halves2bfloat162(h0, h1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tc_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tc_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct TcItem {
+  int b, g0, s0, ns, k, p0, p1, rows, x0, nch, pj0, pj1;   // x0: p0 rounded down to 8 tokens (TMA needs 16-byte
+};                                                          // aligned global addresses); tokens < p0 are masked out
+// item id -> (segment tile, cluster, channel split); identical in every warp role
+__device__ __forceinline__ TcItem tc_item(int id, const int* __restrict__ tile_tbl, const int* __restrict__ cl_ptr, int K,
+                                          int J, int P) {
+  TcItem it;
+  const int j = id % J, rest = id / J;
+  it.k = rest % K;
+  const int tt = rest / K;
+  const int4 t = *reinterpret_cast<const int4*>(tile_tbl + 4 * tt);
+  it.b = t.x; it.g0 = t.y; it.s0 = t.z; it.ns = t.w;
+  it.p0 = cl_ptr[(size_t)it.b * (K + 1) + it.k];
+  it.p1 = cl_ptr[(size_t)it.b * (K + 1) + it.k + 1];
+  it.rows = it.p1 - it.p0;
+  it.x0 = it.p0 & ~7;
+  it.nch = (it.p1 - it.x0 + kTcTokChunk - 1) / kTcTokChunk;
+  it.pj0 = (int)((long long)j * P / J);
+  it.pj1 = (int)((long long)(j + 1) * P / J);
+  return it;
+}
+
+template <typename OutT> struct TcCvt;
+template <> struct TcCvt<double> {
+  static __device__ __forceinline__ void st4(uint32_t a, double x0, double x1, double x2, double x3) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x0), "d"(x1) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(x2), "d"(x3) : "memory");
+  }
+  static constexpr uint32_t kStep = 32;   // bytes per 4 values
+};
+template <> struct TcCvt<float> {
+  static __device__ __forceinline__ void st4(uint32_t a, double x0, double x1, double x2, double x3) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"((float)x0), "f"((float)x1), "f"((float)x2),
+                 "f"((float)x3) : "memory");
+  }
+  static constexpr uint32_t kStep = 16;
+};
+
+template <typename OutT>
+__global__ void __launch_bounds__(kTcThreadsAgg, 1)
+aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __restrict__ tile_tbl,
+                    const int* __restrict__ cl_ptr, const uint16_t* __restrict__ memS, const int* __restrict__ cpred,
+                    int B, int N, int D, int K, int n_items, int J, OutT* __restrict__ out, double* __restrict__ norms) {
+  extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* staging = smem + kTcStages * kTcStageBytes;                       // [4 warps][2 slots][32 rows][row bytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * 2 * 32 * StageRow<OutT>::kBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar_full = smem_u32(bars + 0);      // [kTcStages] A written (2 builder warps) + B landed (TMA)
+  const uint32_t bar_empty = smem_u32(bars + 2);     // [kTcStages] MMAs that read the stage retired
+  const uint32_t bar_tfull = smem_u32(bars + 4);     // [kTcBufs]   accumulator pass complete
+  const uint32_t bar_tempty = smem_u32(bars + 8);    // [kTcBufs]   accumulator drained by the 4 epilogue warps
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = (D + kTcPassN - 1) / kTcPassN;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTcStages; ++i) { mbar_init(bar_full + 8 * i, 3); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kTcBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rt) : "memory");
+      uint32_t stage = 0, phase = 0;
+      for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
+        const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+        if (it.rows == 0) continue;
+        const int n_inst = P + (it.pj1 - it.pj0);
+        for (int inst = 0; inst < n_inst; ++inst) {
+          const int pass = inst < P ? inst : it.pj0 + inst - P;
+          for (int c = 0; c < it.nch; ++c) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t sb = smem_u32(smem + stage * kTcStageBytes) + kTcTileBytes;
+            const uint32_t fb = bar_full + 8 * stage;
+            mbar_arrive_expect_tx(fb, 3 * kTcTileBytes);
+#pragma unroll
+            for (int pl = 0; pl < 3; ++pl)
+              tma_load_2d(sb + pl * kTcTileBytes, &map_rt, fb, it.x0 + c * kTcTokChunk, (pl * B + it.b) * D + pass * kTcPassN);
+            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, ti = 0;
+      for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
+        const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+        if (it.rows == 0) continue;
+        const int n_inst = P + (it.pj1 - it.pj0);
+        for (int inst = 0; inst < n_inst; ++inst, ++ti) {
+          const int pass = inst < P ? inst : it.pj0 + inst - P;
+          const int width = min(kTcPassN, D - pass * kTcPassN);
+          // kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 @17, M>>4 @24
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) |
+                                 ((uint32_t)(kTcSegTile >> 4) << 24);
+          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+          mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kTcPassN;
+          for (int c = 0; c < it.nch; ++c) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * kTcStageBytes);
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const int nk = (min(kTcTokChunk, it.p1 - it.x0 - c * kTcTokChunk) + 15) >> 4;
+            for (int kk = 0; kk < nk; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+#pragma unroll
+              for (int pl = 0; pl < 3; ++pl)   // lo, mid, hi: small terms first
+                tc_mma_bf16(d_tmem, adesc + adv, umma_desc_sw128(sa + (1 + pl) * kTcTileBytes) + adv, idesc,
+                            (c | kk | pl) != 0);
+            }
+            tc_commit(bar_empty + 8 * stage);
+            if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(bar_tfull + 8 * buf);
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== mask-tile builders (64 threads) =====================
+    const int u = threadIdx.x - 192;
+    uint32_t stage = 0, phase = 0;
+    for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
+      const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+      if (it.rows == 0) continue;
+      const int ngrp = (it.ns + 7) >> 3;
+      const int n_inst = P + (it.pj1 - it.pj0);
+      uint32_t wlo[2][4];   // cached membership words of this thread's two (group, 8-token) cells: 8 x u16 each
+      int cached_c = -1;
+      for (int inst = 0; inst < n_inst; ++inst) {
+        for (int c = 0; c < it.nch; ++c) {
+          if (c != cached_c) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int q = u + 64 * r, g = q >> 3, c8 = q & 7;
+              const int i0 = it.x0 + c * kTcTokChunk + c8 * 8;
+              const uint16_t* src = memS + (size_t)(it.g0 + g) * N;
+#pragma unroll
+              for (int t = 0; t < 8; t += 2) {
+                uint32_t a = 0, bb = 0;
+                if (g < ngrp) {
+                  if (i0 + t >= it.p0 && i0 + t < it.p1) a = src[i0 + t];
+                  if (i0 + t + 1 >= it.p0 && i0 + t + 1 < it.p1) bb = src[i0 + t + 1];
+                }
+                wlo[r][t >> 1] = a | (bb << 16);
+              }
+            }
+            cached_c = c;
+          }
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * kTcStageBytes);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int q = u + 64 * r, g = q >> 3, c8 = q & 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // row = 8 g + j of the SWIZZLE_128B K-major tile: 128-byte row, 16-byte chunk c8 stored at c8 ^ (row & 7)
+              uint32_t o[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const uint32_t wv = wlo[r][h];
+                o[h] = (((wv >> j) & 1u) ? 0x3F80u : 0u) | (((wv >> (16 + j)) & 1u) ? 0x3F800000u : 0u);
+              }
+              const uint32_t addr = sa + g * 1024 + j * 128 + ((c8 ^ j) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            }
+          }
+          tc_fence_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+          if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: thread = segment row (TMEM lane) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t rowb = StageRow<OutT>::kBytes;
+    const uint32_t stg = smem_u32(staging) + (uint32_t)(warp - 2) * 2 * 32 * rowb + lane * rowb;   // + slot * 32 * rowb
+    const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t ti = 0, sidx = 0;
+    for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
+      const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+      const bool valid = row < it.ns;
+      const int s = it.s0 + row;
+      OutT* orow = out + ((size_t)(valid ? s : it.s0) * K + it.k) * D;
+      double sc = 0.0;
+      if (it.rows > 0) {
+        // ---- norm sweep ----
+        double ssq = 0.0;
+        for (int pass = 0; pass < P; ++pass, ++ti) {
+          const int width = min(kTcPassN, D - pass * kTcPassN);
+          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+          mbar_wait(bar_tfull + 8 * buf, use & 1);
+          tc_fence_after();
+          for (int cc = 0; cc * 32 < width; ++cc) {
+            uint32_t v[32];
+            tc_ld32(tlane + buf * kTcPassN + cc * 32, v);
+            const int nb = min(32, width - cc * 32);
+            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (j < nb) {
+                const float a = __uint_as_float(v[j]), b2 = __uint_as_float(v[j + 1]);
+                const float c2 = __uint_as_float(v[j + 2]), d2 = __uint_as_float(v[j + 3]);
+                f0 = fmaf(a, a, f0); f1 = fmaf(b2, b2, f1); f2 = fmaf(c2, c2, f2); f3 = fmaf(d2, d2, f3);
+              }
+            }
+            ssq += (double)((f0 + f1) + (f2 + f3));
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        const double nrm = sqrt(ssq);
+        if (valid) {
+          if (it.pj0 == 0) norms[(size_t)s * K + it.k] = nrm;
+          sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cpred[s]), kEpsTc));
+        }
+      } else if (valid && it.pj0 == 0) {
+        norms[(size_t)s * K + it.k] = 0.0;
+      }
+      // ---- write sweep ----
+      for (int pass = it.pj0; pass < it.pj1; ++pass) {
+        const int width = min(kTcPassN, D - pass * kTcPassN);
+        uint32_t buf = 0;
+        if (it.rows > 0) {
+          buf = ti % kTcBufs;
+          mbar_wait(bar_tfull + 8 * buf, (ti / kTcBufs) & 1);
+          tc_fence_after();
+        }
+        for (int cc = 0; cc * 32 < width; ++cc, ++sidx) {
+          uint32_t v[32];
+          if (it.rows > 0) {
+            tc_ld32(tlane + buf * kTcPassN + cc * 32, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+          const int nb = min(32, width - cc * 32);
+          tc_bulk_wait_read1();                                   // the store issued two pieces ago has left its slot
+          const uint32_t sl = stg + (sidx & 1u) * 32 * rowb;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            TcCvt<OutT>::st4(sl + (j >> 2) * TcCvt<OutT>::kStep, (double)__uint_as_float(v[j]) * sc,
+                             (double)__uint_as_float(v[j + 1]) * sc, (double)__uint_as_float(v[j + 2]) * sc,
+                             (double)__uint_as_float(v[j + 3]) * sc);
+          tc_fence_async_smem();
+          if (valid) tc_bulk_store(orow + (size_t)pass * kTcPassN + cc * 32, sl, (uint32_t)nb * (uint32_t)sizeof(OutT));
+          tc_bulk_commit();
+        }
+        if (it.rows > 0) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          ++ti;
+        }
+      }
+    }
+    tc_bulk_wait_read0();   // shared memory must outlive the last asynchronous stores
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+bool agg_tc_supported(int N, int D, int K) {
+  const char* e = getenv("SEGVLAD_AGG_TC");   // "0" selects the SIMT kernel of aggregate.cu (kept as a cross-check)
+  const bool on = !(e && e[0] == '0');
+  return on && N >= 1 && K >= 1 && D >= 16 && D % 16 == 0 && D <= 65536;
+}
+
+template <typename OutT>
+static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, int J, int grid, cudaStream_t st) {
+  const size_t smem = agg_tc_smem<OutT>();
+  SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
+  aggregate_tc_kernel<OutT><<<grid, kTcThreadsAgg, smem, st>>>(map, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K,
+                                                             n_items, J, reinterpret_cast<OutT*>(a.out), a.norms);
+  prof_end(pslot, st);
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+int agg_tc_run(const AggTcArgs& a, cudaStream_t st) {
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SV_CHECK_CUDA(cudaGetDevice(&dev));
+    SV_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int Np = agg_tc_np(a.N);
+  // segment tiles: 16 consecutive 8-segment groups of one image (group numbering = aggregate.cu's group table)
+  const int max_tiles = agg_tc_max_tiles(a.B, a.S_total);
+  int* h = (int*)malloc(sizeof(int) * 4 * (size_t)max_tiles);
+  SV_REQUIRE(h, "aggregate: host malloc failed");
+  int nt = 0, g = 0;
+  for (int b = 0; b < a.B; ++b) {
+    const int s0 = a.seg_offsets_host[b], Si = a.seg_offsets_host[b + 1] - s0;
+    for (int t0 = 0; t0 < Si; t0 += kTcSegTile) {
+      h[4 * nt + 0] = b; h[4 * nt + 1] = g + t0 / 8; h[4 * nt + 2] = s0 + t0; h[4 * nt + 3] = min(kTcSegTile, Si - t0);
+      ++nt;
+    }
+    g += (Si + 7) / 8;
+  }
+  cudaError_t e = cudaMemcpyAsync(a.tile_tbl, h, sizeof(int) * 4 * (size_t)nt, cudaMemcpyHostToDevice, st);
+  free(h);
+  SV_CHECK_CUDA(e);
+  if (nt == 0) return SEGVLAD_OK;
+
+  rt_planes_kernel<<<dim3(Np / 64, (a.D + 31) / 32, a.B), 256, 0, st>>>(a.R, a.cl_tok, a.B, a.N, a.D, Np, a.RT);
+  SV_CHECK_LAUNCH();
+
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SEGVLAD_ECUDA; }
+  CUtensorMap map;
+  cuuint64_t dims[2] = {(cuuint64_t)Np, (cuuint64_t)3 * a.B * a.D};
+  cuuint64_t strides[1] = {(cuuint64_t)Np * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kTcTokChunk, (cuuint32_t)kTcPassN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.RT, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SEGVLAD_ECUDA; }
+
+  const int P = (a.D + kTcPassN - 1) / kTcPassN;
+  int J = 1;
+  while ((long long)nt * a.K * J < 2ll * num_sms && J * 2 <= P) J *= 2;   // few items: split the write sweep over channels
+  const long long n_items = (long long)nt * a.K * J;
+  SV_REQUIRE(n_items < (1ll << 31), "aggregate: too many work items");
+  const int grid = (int)(n_items < num_sms ? n_items : num_sms);
+  return a.out_dtype == SEGVLAD_OUT_F64 ? launch_tc<double>(a, map, (int)n_items, J, grid, st)
+                                        : launch_tc<float>(a, map, (int)n_items, J, grid, st);
+}
+
+}  // namespace segvlad

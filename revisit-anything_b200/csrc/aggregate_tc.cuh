@@ -1,0 +1,35 @@
+// Tensor-core (tcgen05) formulation of the masked residual aggregation -- interface between aggregate.cu (driver,
+// membership / cluster-list preparation) and aggregate_tc.cu (kernels).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace segvlad {
+
+constexpr int kTcSegTile = 128;   // segments per MMA tile (M)
+constexpr int kTcTokChunk = 64;   // tokens per K chunk (one 128-byte swizzle row of bf16)
+constexpr int kTcPassN = 128;     // descriptor channels per accumulator pass (N)
+
+struct AggTcArgs {
+  const float* R;             // [B][N][D] fp32 residual rows (token-major)
+  const int* cl_ptr;          // [B][K+1] cluster boundaries in the label-sorted token order
+  const int* cl_tok;          // [B][N]   label-sorted token ids
+  const uint16_t* memS;       // [n_groups][N] membership words (bit j = segment 8*g + j), label-sorted order
+  const int* cpred;           // [S_total] number of non-empty clusters per segment
+  double* norms;              // [S_total][K] block norms (for the row-norm fix-up)
+  const int32_t* seg_offsets_host;
+  int B, N, D, K, S_total;
+  void* out;                  // [S_total][K*D]
+  int out_dtype;
+  __nv_bfloat16* RT;          // workspace: [3 planes][B][D][Np] transposed, label-sorted bf16 split of R
+  int* tile_tbl;              // workspace: [n_tiles][4] = image, first group, first segment, #segments
+};
+
+inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcTokChunk); }
+inline size_t agg_tc_rt_elems(int B, int N, int D) { return (size_t)3 * B * D * agg_tc_np(N); }
+inline int agg_tc_max_tiles(int B, int S_total) { return S_total / kTcSegTile + B; }
+bool agg_tc_supported(int N, int D, int K);
+int agg_tc_run(const AggTcArgs& a, cudaStream_t st);   // returns SEGVLAD_* status
+
+}  // namespace segvlad
