@@ -14,8 +14,9 @@
 //     by two builder warps from the membership words, B = [128 channels x 64 tokens] x 3 planes by TMA, D = fp32
 //     accumulators in TMEM (4 buffers of 128 columns);
 //   * the block norm needs all D channels but TMEM holds 512 of them, so the contraction is issued twice -- a norm
-//     sweep (TMEM -> sum of squares, no stores) and a write sweep (TMEM -> x scale -> fp64 -> shared staging -> bulk
-//     stores).  The tensor work is ~10 % of the write time, the operand re-read comes from L2;
+//     sweep (TMEM -> sum of squares, no stores) and a write sweep (TMEM -> x scale -> fp64 -> 256-bit global stores;
+//     r1: 256-byte bulk stores through a staging buffer were bound by the TMA request rate, ~6 k requests per item).
+//     The tensor work is ~10 % of the write time, the operand re-read comes from L2;
 //   * thread = segment row (TMEM lane), so norms and scales never leave the thread: no reductions, no CTA barriers.
 // Accumulation is fp32 in TMEM (truncating adds, measured ~4e-8 relative per MMA): <= 3 * n_k / 16 MMAs per element,
 // i.e. ~1e-6 relative for the largest clusters -- inside the 1e-5 descriptor tolerance; the planes are accumulated
@@ -29,19 +30,13 @@
 namespace segvlad {
 
 constexpr int kTcThreadsAgg = 256;
-constexpr int kTcStages = 2;
+constexpr int kTcStages = 3;
 constexpr uint32_t kTcTileBytes = kTcSegTile * kTcTokChunk * 2;          // 16 KB: one [128 x 64] bf16 operand tile
 constexpr uint32_t kTcStageBytes = 4 * kTcTileBytes;                     // A + 3 B planes
 constexpr int kTcBufs = 512 / kTcPassN;                                  // TMEM accumulator buffers
 constexpr double kEpsTc = 1e-12;
 
-template <typename OutT> struct StageRow;   // bytes of one staged row piece (32 values) + 16 B pad (bank spread)
-template <> struct StageRow<double> { static constexpr uint32_t kBytes = 32 * 8 + 16; };
-template <> struct StageRow<float> { static constexpr uint32_t kBytes = 32 * 4 + 16; };
-
-template <typename OutT> __host__ __device__ constexpr size_t agg_tc_smem() {
-  return 1024 + (size_t)kTcStages * kTcStageBytes + (size_t)4 * 2 * 32 * StageRow<OutT>::kBytes + 256;
-}
+__host__ __device__ constexpr size_t agg_tc_smem() { return 1024 + (size_t)kTcStages * kTcStageBytes + 256; }
 
 // ------------------------------------------------------------------------------------------------
 // R [B][N][D] fp32 -> RT [3][B][D][Np] bf16 (lo, mid, hi), columns in label-sorted order, zero padded to Np.
@@ -80,12 +75,6 @@ rt_planes_kernel(const float* __restrict__ R, const int* __restrict__ cl_tok, in
 }
 
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tc_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tc_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct TcItem {
@@ -110,20 +99,79 @@ __device__ __forceinline__ TcItem tc_item(int id, const int* __restrict__ tile_t
   return it;
 }
 
-template <typename OutT> struct TcCvt;
-template <> struct TcCvt<double> {
-  static __device__ __forceinline__ void st4(uint32_t a, double x0, double x1, double x2, double x3) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(x0), "d"(x1) : "memory");
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(x2), "d"(x3) : "memory");
+// tcgen05.ld split into issue + wait so that the next 32 columns load while the current ones are processed.  The wait
+// takes the destination registers as in/out operands: the compiler must not consume them before the wait.
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ float tc_sumsq(const uint32_t (&v)[32], int nb) {
+  float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    if (j < nb) {
+      const float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+      const float c = __uint_as_float(v[j + 2]), d = __uint_as_float(v[j + 3]);
+      f0 = fmaf(a, a, f0); f1 = fmaf(b, b, f1); f2 = fmaf(c, c, f2); f3 = fmaf(d, d, f3);
+    }
   }
-  static constexpr uint32_t kStep = 32;   // bytes per 4 values
+  return (f0 + f1) + (f2 + f3);
+}
+
+// Scaled accumulator piece (32 consecutive channels of one block row) -> global memory with 256-bit stores: every
+// lane writes whole 32-byte sectors of its own row, so the row-per-lane pattern costs no write amplification.
+template <typename OutT> struct TcOut;
+template <> struct TcOut<double> {
+  static __device__ __forceinline__ void store(double* p, const uint32_t (&v)[32], double sc, int nb) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (j < nb)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p + j), "d"((double)__uint_as_float(v[j]) * sc),
+                     "d"((double)__uint_as_float(v[j + 1]) * sc), "d"((double)__uint_as_float(v[j + 2]) * sc),
+                     "d"((double)__uint_as_float(v[j + 3]) * sc) : "memory");
+    }
+  }
+  static __device__ __forceinline__ void zero16(double* p) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      asm volatile("st.global.v4.f64 [%0], {%1, %1, %1, %1};" ::"l"(p + j), "d"(0.0) : "memory");
+  }
 };
-template <> struct TcCvt<float> {
-  static __device__ __forceinline__ void st4(uint32_t a, double x0, double x1, double x2, double x3) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"((float)x0), "f"((float)x1), "f"((float)x2),
-                 "f"((float)x3) : "memory");
+template <> struct TcOut<float> {
+  static __device__ __forceinline__ void store(float* p, const uint32_t (&v)[32], double sc, int nb) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      if (j < nb)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p + j),
+                     "f"((float)((double)__uint_as_float(v[j]) * sc)), "f"((float)((double)__uint_as_float(v[j + 1]) * sc)),
+                     "f"((float)((double)__uint_as_float(v[j + 2]) * sc)), "f"((float)((double)__uint_as_float(v[j + 3]) * sc)),
+                     "f"((float)((double)__uint_as_float(v[j + 4]) * sc)), "f"((float)((double)__uint_as_float(v[j + 5]) * sc)),
+                     "f"((float)((double)__uint_as_float(v[j + 6]) * sc)), "f"((float)((double)__uint_as_float(v[j + 7]) * sc))
+                     : "memory");
+    }
   }
-  static constexpr uint32_t kStep = 16;
+  static __device__ __forceinline__ void zero16(float* p) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 8)
+      asm volatile("st.global.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p + j), "f"(0.f) : "memory");
+  }
 };
 
 template <typename OutT>
@@ -133,13 +181,12 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
                     int B, int N, int D, int K, int n_items, int J, OutT* __restrict__ out, double* __restrict__ norms) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + kTcStages * kTcStageBytes;                       // [4 warps][2 slots][32 rows][row bytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 4 * 2 * 32 * StageRow<OutT>::kBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar_full = smem_u32(bars + 0);      // [kTcStages] A written (2 builder warps) + B landed (TMA)
-  const uint32_t bar_empty = smem_u32(bars + 2);     // [kTcStages] MMAs that read the stage retired
-  const uint32_t bar_tfull = smem_u32(bars + 4);     // [kTcBufs]   accumulator pass complete
-  const uint32_t bar_tempty = smem_u32(bars + 8);    // [kTcBufs]   accumulator drained by the 4 epilogue warps
+  const uint32_t bar_empty = smem_u32(bars + 4);     // [kTcStages] MMAs that read the stage retired
+  const uint32_t bar_tfull = smem_u32(bars + 8);     // [kTcBufs]   accumulator pass complete
+  const uint32_t bar_tempty = smem_u32(bars + 12);   // [kTcBufs]   accumulator drained by the 4 epilogue warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = (D + kTcPassN - 1) / kTcPassN;
 
@@ -279,89 +326,83 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
     // ===================== epilogue warps: thread = segment row (TMEM lane) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const uint32_t rowb = StageRow<OutT>::kBytes;
-    const uint32_t stg = smem_u32(staging) + (uint32_t)(warp - 2) * 2 * 32 * rowb + lane * rowb;   // + slot * 32 * rowb
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t ti = 0, sidx = 0;
+    uint32_t ti = 0;
     for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
       const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
       const bool valid = row < it.ns;
       const int s = it.s0 + row;
       OutT* orow = out + ((size_t)(valid ? s : it.s0) * K + it.k) * D;
-      double sc = 0.0;
-      if (it.rows > 0) {
-        // ---- norm sweep ----
-        double ssq = 0.0;
-        for (int pass = 0; pass < P; ++pass, ++ti) {
-          const int width = min(kTcPassN, D - pass * kTcPassN);
-          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-          mbar_wait(bar_tfull + 8 * buf, use & 1);
-          tc_fence_after();
-          for (int cc = 0; cc * 32 < width; ++cc) {
-            uint32_t v[32];
-            tc_ld32(tlane + buf * kTcPassN + cc * 32, v);
-            const int nb = min(32, width - cc * 32);
-            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (j < nb) {
-                const float a = __uint_as_float(v[j]), b2 = __uint_as_float(v[j + 1]);
-                const float c2 = __uint_as_float(v[j + 2]), d2 = __uint_as_float(v[j + 3]);
-                f0 = fmaf(a, a, f0); f1 = fmaf(b2, b2, f1); f2 = fmaf(c2, c2, f2); f3 = fmaf(d2, d2, f3);
-              }
-            }
-            ssq += (double)((f0 + f1) + (f2 + f3));
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        }
-        const double nrm = sqrt(ssq);
+      if (it.rows == 0) {
+        // empty cluster: the block is zero for every segment
         if (valid) {
-          if (it.pj0 == 0) norms[(size_t)s * K + it.k] = nrm;
-          sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cpred[s]), kEpsTc));
+          if (it.pj0 == 0) norms[(size_t)s * K + it.k] = 0.0;
+          const int d_beg = it.pj0 * kTcPassN, d_end = min(D, it.pj1 * kTcPassN);
+          for (int d = d_beg; d < d_end; d += 16) TcOut<OutT>::zero16(orow + d);
         }
-      } else if (valid && it.pj0 == 0) {
-        norms[(size_t)s * K + it.k] = 0.0;
+        continue;
       }
-      // ---- write sweep ----
-      for (int pass = it.pj0; pass < it.pj1; ++pass) {
+      // ---- norm sweep: sum of squares of the whole block row (fp32 products, fp64 accumulation per 32 columns) ----
+      double ssq = 0.0;
+      for (int pass = 0; pass < P; ++pass, ++ti) {
         const int width = min(kTcPassN, D - pass * kTcPassN);
-        uint32_t buf = 0;
-        if (it.rows > 0) {
-          buf = ti % kTcBufs;
-          mbar_wait(bar_tfull + 8 * buf, (ti / kTcBufs) & 1);
-          tc_fence_after();
-        }
-        for (int cc = 0; cc * 32 < width; ++cc, ++sidx) {
-          uint32_t v[32];
-          if (it.rows > 0) {
-            tc_ld32(tlane + buf * kTcPassN + cc * 32, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0u;
+        const int np = (width + 31) >> 5;
+        const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+        mbar_wait(bar_tfull + 8 * buf, use & 1);
+        tc_fence_after();
+        const uint32_t tcol = tlane + buf * kTcPassN;
+        uint32_t va[32], vb[32];
+        tc_ld32_issue(tcol, va);
+        tc_ld_wait(va);
+#pragma unroll 1
+        for (int cc = 0; cc < np; cc += 2) {
+          if (cc + 1 < np) tc_ld32_issue(tcol + (cc + 1) * 32, vb);      // next piece loads while this one is reduced
+          ssq += (double)tc_sumsq(va, min(32, width - cc * 32));
+          if (cc + 1 < np) {
+            tc_ld_wait(vb);
+            if (cc + 2 < np) tc_ld32_issue(tcol + (cc + 2) * 32, va);
+            ssq += (double)tc_sumsq(vb, min(32, width - (cc + 1) * 32));
+            if (cc + 2 < np) tc_ld_wait(va);
           }
-          const int nb = min(32, width - cc * 32);
-          tc_bulk_wait_read1();                                   // the store issued two pieces ago has left its slot
-          const uint32_t sl = stg + (sidx & 1u) * 32 * rowb;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            TcCvt<OutT>::st4(sl + (j >> 2) * TcCvt<OutT>::kStep, (double)__uint_as_float(v[j]) * sc,
-                             (double)__uint_as_float(v[j + 1]) * sc, (double)__uint_as_float(v[j + 2]) * sc,
-                             (double)__uint_as_float(v[j + 3]) * sc);
-          tc_fence_async_smem();
-          if (valid) tc_bulk_store(orow + (size_t)pass * kTcPassN + cc * 32, sl, (uint32_t)nb * (uint32_t)sizeof(OutT));
-          tc_bulk_commit();
         }
-        if (it.rows > 0) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-          ++ti;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      }
+      const double nrm = sqrt(ssq);
+      double sc = 0.0;
+      if (valid) {
+        if (it.pj0 == 0) norms[(size_t)s * K + it.k] = nrm;
+        sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cpred[s]), kEpsTc));
+      }
+      // ---- write sweep: accumulator x scale -> fp64 -> 32-byte vector stores (each lane fills whole sectors of its row) ----
+      for (int pass = it.pj0; pass < it.pj1; ++pass, ++ti) {
+        const int width = min(kTcPassN, D - pass * kTcPassN);
+        const int np = (width + 31) >> 5;
+        const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+        mbar_wait(bar_tfull + 8 * buf, use & 1);
+        tc_fence_after();
+        const uint32_t tcol = tlane + buf * kTcPassN;
+        OutT* op = orow + (size_t)pass * kTcPassN;
+        uint32_t va[32], vb[32];
+        tc_ld32_issue(tcol, va);
+        tc_ld_wait(va);
+#pragma unroll 1
+        for (int cc = 0; cc < np; cc += 2) {
+          if (cc + 1 < np) tc_ld32_issue(tcol + (cc + 1) * 32, vb);
+          if (valid) TcOut<OutT>::store(op + cc * 32, va, sc, min(32, width - cc * 32));
+          if (cc + 1 < np) {
+            tc_ld_wait(vb);
+            if (cc + 2 < np) tc_ld32_issue(tcol + (cc + 2) * 32, va);
+            if (valid) TcOut<OutT>::store(op + (cc + 1) * 32, vb, sc, min(32, width - (cc + 1) * 32));
+            if (cc + 2 < np) tc_ld_wait(va);
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       }
     }
-    tc_bulk_wait_read0();   // shared memory must outlive the last asynchronous stores
   }
   tc_fence_before();
   __syncthreads();
@@ -380,7 +421,7 @@ bool agg_tc_supported(int N, int D, int K) {
 
 template <typename OutT>
 static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, int J, int grid, cudaStream_t st) {
-  const size_t smem = agg_tc_smem<OutT>();
+  const size_t smem = agg_tc_smem();
   SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   aggregate_tc_kernel<OutT><<<grid, kTcThreadsAgg, smem, st>>>(map, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K,
