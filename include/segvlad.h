@@ -95,8 +95,9 @@ int segvlad_mask_to_membership(const uint8_t* masks, int S, int Hm, int Wm, int 
  * Matching: exhaustive squared-L2 kNN of query-segment descriptors against a (shard of the)
  * reference bank.  Replaces faiss.IndexFlatL2.add/search at place_rec_main.py:53-61.
  *
- * A "bank" is the resident, kernel-ready form of an [n, D] fp32 descriptor matrix: two bf16 planes
- * (hi, mid: x ~= hi + mid to 2^-17 relative) padded to a multiple of 64 columns, and fp32 squared norms.
+ * A "bank" is the resident, kernel-ready form of an [n, D] fp32 descriptor matrix: one fp16 plane (each row scaled by
+ * a power of two, padded to a multiple of 64 columns) for the tensor-core scan, per-row fp32 squared norm / scale /
+ * rounding residual (the scan's error bound), and the fp32 rows for the exact re-score of the surviving candidates.
  */
 size_t segvlad_bank_bytes(int n, int D);
 int segvlad_bank_prepare(const float* x, int n, int D, void* bank, void* stream);
@@ -126,6 +127,12 @@ int segvlad_knn_from_host(const float* q_host, int Nq, const float* r_host, int 
 int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, int64_t row_offset, int D, int k,
                      float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
                      void* stream);
+
+/* Test hook for the scan's error model (Nr <= 4096): the approximate d2 the single fp16 tensor-core pass assigns to
+ * every (query, reference) pair, approx_out [Nq, Nr], and the per-query bound E the filter assumes on
+ * |approx - fp32 value|, bound_out [Nq].  Workspace as for segvlad_knn. */
+int segvlad_knn_debug_approx(const void* qbank, int Nq, const void* rbank, int Nr, int D, float* approx_out,
+                             float* bound_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* k-way merge of per-shard results after the all-gather: parts are [G, Nq, k]. */
 int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, int Nq, int k,

@@ -4,22 +4,33 @@
 // d2 = ||q||^2 + ||r||^2 - 2<q,r>, clamped at 0, k smallest ascending).
 //
 // Structure
-//   bank_prepare        fp32 [n,D] -> bf16 hi / mid planes (x ~= hi + mid, 2^-17 rel.) + fp32 ||x||^2
-//   knn_tc_filter       persistent tcgen05 kernel: all-pairs <q,r> = hi.hi + hi.mid + mid.hi on the tensor
-//                       cores (kind::f16, bf16 in, fp32 accumulate in TMEM), TMA-fed 2-stage smem ring,
-//                       double-buffered 128x256 accumulators; the epilogue turns each inner product into d2,
-//                       compares it with the row's running threshold tau and appends survivors to the
-//                       row's candidate list (the all-pairs matrix is never written to HBM)
+//   bank_prepare        fp32 [n,D] -> ONE fp16 plane of the row scaled by a power of two (row maximum in [2^14, 2^15)),
+//                       fp32 ||x||^2, and the row's exact rounding residual rho = ||x - fp16(x)||_2; the bank keeps the
+//                       running maxima of rho and ||x|| (error model of the filter below)
+//   knn_tc_filter       persistent tcgen05 kernel: all-pairs <q,r> in ONE fp16 MMA pass (kind::f16, fp32 accumulate in
+//                       TMEM), TMA-fed shared-memory ring, double-buffered 128x256 accumulators; the epilogue turns each
+//                       inner product into an approximate d2, compares it with the row's threshold and appends
+//                       survivors to the row's candidate list (the all-pairs matrix is never written to HBM)
 //   knn_simt_filter     same epilogue behind a plain fp32 FFMA tile kernel (cross-check path)
-//   knn_refine          per row: bitonic-select the k best candidates, tighten tau; final pass sorts and
-//                       writes (d2, global index) ascending with (d2, idx) tie order
+//   knn_refine          per row: radix-select the k-th best candidate, drop what can no longer be a result
+//   knn_rescore         exact fp32 re-evaluation of the surviving candidates on the resident fp32 rows
 //   merge_topk          k-way merge of per-shard lists after the all-gather
 //
-// The reference bank is scanned in rounds of geometrically growing chunks: after a chunk, tau = current
+// Exactness of the single fp16 pass.  |<q,r> - <q^,r^>| <= ||q|| rho_r + rho_q ||r^|| (Cauchy-Schwarz on
+// q.(r - r^) + (q - q^).r^), plus the fp32 accumulation error of the TMEM chain (<= c_acc ||q|| ||r||), so every
+// approximate d2 of a query row is within E_row = 2 (||q|| rho_max + rho_q (n_max + rho_max) + c_acc ||q|| n_max) (+
+// epilogue rounding) of the fp32 value the re-score computes.  If T is the k-th smallest APPROXIMATE d2 seen so far, the
+// exact k-th is <= T + E, so a reference with approximate d2 > T + 2E can never be among the k nearest: the filter keeps
+// `approx <= T + 2E`, the survivors (k + a few) are re-scored exactly and the k best of those are the exact answer.
+// For unit-norm 1536-D descriptors 2E ~ 1.7e-3 against a d2 spread of ~0.05: ~10 % more candidates than k.
+//
+// The reference bank is scanned in rounds of geometrically growing chunks: after a chunk, T = current
 // k-th best, so a later chunk of n refs leaves ~ n*k/seen survivors per row.  Buffers overflowing
-// (adversarially ordered banks) raise a flag; the host then re-runs with chunks <= C - k (cannot overflow).
+// (adversarially ordered or massively duplicated banks) raise a flag; the host then re-runs that query block with
+// chunks <= C - k and an exact re-score + exact (d2, idx) selection of k after every round (cannot overflow).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,10 +40,9 @@ namespace segvlad {
 
 constexpr int kCandCap = 4096;     // candidate slots per query row
 constexpr int kMaxK = 1024;
-constexpr int kRescoreMargin = 32;  // extra candidates kept by the tensor-core selection before exact re-scoring
 constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
-constexpr int kTcThreads = 192;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int kTcThreads = 320;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quarter)
 
 struct SelState {
   float* tau;      // [rows] current k-th best d2 (+inf until k candidates seen)
@@ -61,88 +71,143 @@ __device__ __forceinline__ void cand_append(const SelState& s, int row, int col,
 // ------------------------------------------------------------------------------------------------
 // bank preparation: one warp per row
 struct BankView {
-  const __nv_bfloat16* hi; const __nv_bfloat16* mid; const float* norms; const float* x32; int Dp;
+  const __half* h16;      // [n][Dp] fp16 plane of the row scaled by 2^(14 - e_row) (sub-normal results flushed to 0)
+  const float* norms;     // [n] ||x||^2 (fp32)
+  const float4* meta;     // [n] {||x||^2, 2^(e_row - 14), rho = ||x - h16 / scale||_2 (rounded up), ||x|| (rounded up)}
+  const unsigned* stats;  // [0] max rho, [1] max ||x|| over the prepared rows (bit patterns of non-negative floats)
+  const float* x32;       // [n][D] fp32 rows: exact re-scoring of the selected candidates
+  int Dp;
 };
 static inline int padded_dim(int D) { return (int)align_up((size_t)D, kTileK); }
 static BankView bank_view(const void* bank, int n, int D) {
   Carver c(const_cast<void*>(bank));
   BankView v;
   v.Dp = padded_dim(D);
-  v.hi = c.take<__nv_bfloat16>((size_t)n * v.Dp);
-  v.mid = c.take<__nv_bfloat16>((size_t)n * v.Dp);
+  v.h16 = c.take<__half>((size_t)n * v.Dp);
   v.norms = c.take<float>(n);
-  v.x32 = c.take<float>((size_t)n * D);  // fp32 rows: exact re-scoring of the selected candidates
+  v.meta = c.take<float4>(n);
+  v.stats = c.take<unsigned>(64);
+  v.x32 = c.take<float>((size_t)n * D);
+  return v;
+}
+struct BankOut { __half* h16; float* norms; float4* meta; unsigned* stats; float* x32; int Dp; };
+static BankOut bank_out(const BankView& v) {
+  return {const_cast<__half*>(v.h16), const_cast<float*>(v.norms), const_cast<float4*>(v.meta),
+          const_cast<unsigned*>(v.stats), const_cast<float*>(v.x32), v.Dp};
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 
-__global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, int Dp,
-                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                    float* __restrict__ norms, float* __restrict__ x32) {
+// Second half of the row preparation; the fp32 values of the row already sit in x32 (written by this warp's lanes at
+// the same d stride, or copied there from the host).  ss / mx: this lane's partial sum of squares / maximum |x|.
+__device__ __forceinline__ void bank_finish_row(const BankOut& b, int row, int D, float ss, float mx, int lane) {
+  ss = warp_sum(ss);
+  mx = warp_max(mx);
+  int e = 0;
+  if (mx > 0.f && mx < INFINITY) e = ilogbf(mx);
+  e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  const float sc = __int_as_float((127 + 14 - e) << 23);    // 2^(14 - e): row maximum -> [2^14, 2^15) < fp16 max
+  const float inv = __int_as_float((127 - 14 + e) << 23);
+  const float* xr = b.x32 + (size_t)row * D;
+  __half* hr = b.h16 + (size_t)row * b.Dp;
+  float err2 = 0.f;
+  for (int d = lane; d < b.Dp; d += 32) {
+    const float v = d < D ? xr[d] : 0.f;
+    __half h = __float2half_rn(v * sc);
+    float hf = __half2float(h);
+    if (fabsf(hf) < 6.103515625e-05f) { h = __ushort_as_half((unsigned short)0); hf = 0.f; }   // no fp16 sub-normals
+    const float er = v - hf * inv;      // exact in fp32 (both on v's grid, within a factor of two)
+    err2 = fmaf(er, er, err2);
+    hr[d] = h;
+  }
+  err2 = warp_sum(err2);
+  if (lane == 0) {
+    float rho = sqrtf(err2) * 1.0005f, nr = sqrtf(ss) * 1.000001f;
+    if (!(rho < INFINITY)) rho = 0.f;   // NaN / inf rows: their scores are NaN -> clamped to 0 in both passes
+    if (!(nr < INFINITY)) nr = 0.f;
+    b.norms[row] = ss;
+    b.meta[row] = make_float4(ss, inv, rho, nr);
+    volatile unsigned* vs = b.stats;
+    if (__float_as_uint(rho) > vs[0]) atomicMax(b.stats + 0, __float_as_uint(rho));
+    if (__float_as_uint(nr) > vs[1]) atomicMax(b.stats + 1, __float_as_uint(nr));
+  }
+}
+
+__global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, BankOut b) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* xr = x + (size_t)row * D;
-  float ss = 0.f;
-  for (int d = lane; d < Dp; d += 32) {
-    float v = d < D ? xr[d] : 0.f;
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
-    hi[(size_t)row * Dp + d] = h;
-    mid[(size_t)row * Dp + d] = m;
-    if (d < D) x32[(size_t)row * D + d] = v;
+  float* x32r = b.x32 + (size_t)row * D;
+  float ss = 0.f, mx = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = xr[d];
+    x32r[d] = v;
     ss = fmaf(v, v, ss);
+    mx = fmaxf(mx, fabsf(v));
   }
-  ss = warp_sum(ss);
-  if (lane == 0) norms[row] = ss;
+  bank_finish_row(b, row, D, ss, mx, lane);
 }
 
 // rows [row0, row0+nrows) whose fp32 values already sit in the bank's x32 region (host-streamed path)
-__global__ void bank_prepare_rows_kernel(const float* __restrict__ x32, int row0, int nrows, int D, int Dp,
-                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                         float* __restrict__ norms) {
+__global__ void bank_prepare_rows_kernel(int row0, int nrows, int D, BankOut b) {
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= nrows) return;
   const int row = row0 + r;
-  const float* xr = x32 + (size_t)row * D;
-  float ss = 0.f;
-  for (int d = lane; d < Dp; d += 32) {
-    float v = d < D ? xr[d] : 0.f;
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
-    hi[(size_t)row * Dp + d] = h;
-    mid[(size_t)row * Dp + d] = m;
+  const float* xr = b.x32 + (size_t)row * D;
+  float ss = 0.f, mx = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = xr[d];
     ss = fmaf(v, v, ss);
+    mx = fmaxf(mx, fabsf(v));
   }
-  ss = warp_sum(ss);
-  if (lane == 0) norms[row] = ss;
+  bank_finish_row(b, row, D, ss, mx, lane);
 }
 
-__global__ void bank_prepare_f64_kernel(const double* __restrict__ x, int n, int D, int Dp, int normalize_rows,
-                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ mid,
-                                        float* __restrict__ norms, float* __restrict__ x32) {
+__global__ void bank_prepare_f64_kernel(const double* __restrict__ x, int n, int D, int normalize_rows, BankOut b) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   const double* xr = x + (size_t)row * D;
+  float* x32r = b.x32 + (size_t)row * D;
   double nrm = 1.0;
   if (normalize_rows) {
     double s2 = 0.0;
     for (int d = lane; d < D; d += 32) s2 += xr[d] * xr[d];
     nrm = sqrt(warp_sum(s2));  // no eps: a zero row becomes NaN exactly like normalizeFeat
   }
-  float ss = 0.f;
-  for (int d = lane; d < Dp; d += 32) {
-    float v = d < D ? (float)(normalize_rows ? xr[d] / nrm : xr[d]) : 0.f;
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    __nv_bfloat16 m = __float2bfloat16_rn(v - __bfloat162float(h));
-    hi[(size_t)row * Dp + d] = h;
-    mid[(size_t)row * Dp + d] = m;
-    if (d < D) x32[(size_t)row * D + d] = v;
+  float ss = 0.f, mx = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float v = (float)(normalize_rows ? xr[d] / nrm : xr[d]);
+    x32r[d] = v;
     ss = fmaf(v, v, ss);
+    mx = fmaxf(mx, fabsf(v));
   }
-  ss = warp_sum(ss);
-  if (lane == 0) norms[row] = ss;
+  bank_finish_row(b, row, D, ss, mx, lane);
+}
+
+// Error model of the approximate (single fp16 pass) scores of one query row -- see the header comment.
+struct ErrModel {
+  const float4* qmeta;     // query bank meta
+  const unsigned* rstats;  // reference bank maxima; nullptr: the scores are exact (SIMT path), bound = 0
+  float c_acc;             // fp32 accumulation error of the TMEM chain + the fp32 re-score, relative to ||q|| ||r||
+};
+__device__ __forceinline__ float row_err_bound(const ErrModel& em, int qrow) {
+  if (!em.rstats) return 0.f;
+  const float4 m = em.qmeta[qrow];
+  const float rmax = __uint_as_float(em.rstats[0]), nmax = __uint_as_float(em.rstats[1]);
+  const float nq = m.w, s = nq + nmax;
+  float e = 2.f * (nq * rmax + m.z * (nmax + rmax) + em.c_acc * nq * nmax);
+  e = fmaf(4.8e-7f, s * s, e);          // roundings of the epilogue arithmetic (2^-21 (||q|| + ||r||)^2)
+  return (e < INFINITY) ? e * 1.001f : 0.f;
+}
+static inline float acc_err_const(int D) {
+  return (float)((D / 16 + 32) * ldexp(1.0, -22) + (D / 32 + 8) * ldexp(1.0, -23));
 }
 
 __global__ void row_norms_kernel(const float* __restrict__ x, int n, int D, float* __restrict__ norms) {
@@ -212,19 +277,19 @@ knn_simt_filter_kernel(const float* __restrict__ q, const float* __restrict__ r,
 
 // ------------------------------------------------------------------------------------------------
 // Persistent tcgen05 all-pairs + filter kernel, templated on the CTA-group size.
-//   kCtas == 1 : one CTA per 128 x 256 tile (2-stage ring of 96 KB: Q 128 rows + R 256 rows, hi+mid planes)
+//   kCtas == 1 : one CTA per 128 x 256 tile (4-stage ring of 48 KB: Q 128 rows + R 256 rows of one 64-channel block)
 //   kCtas == 2 : a CTA PAIR (cluster 2x1x1, tcgen05 cta_group::2) per 256 x 256 tile; each CTA stages its own 128
-//                query rows and HALF of the reference tile (3-stage ring of 64 KB), the pair's MMA (M=256) reads
-//                both halves => L2->SM operand traffic per MMA drops by 1/3 (r1 ncu: cta_group::1 needs
-//                64 B/clk/SM at full tensor rate and stalled at ~53 % pipe utilisation)
+//                query rows and HALF of the reference tile (6-stage ring of 32 KB), the pair's MMA (M=256) reads
+//                both halves => L2->SM operand traffic per MMA drops by 1/3
 // grid = min(#tiles, #SMs) CTAs (pairs: even); tile t -> (col_tile = t / n_row_tiles, row_tile = t % n_row_tiles)
 // so concurrently running CTAs share a reference tile through L2 and the bank streams from HBM once.
 template <int kCtas> struct TcCfg;
-template <> struct TcCfg<1> { static constexpr int kStagesT = 2; static constexpr uint32_t kRRows = 256; };
-template <> struct TcCfg<2> { static constexpr int kStagesT = 3; static constexpr uint32_t kRRows = 128; };
-template <int kCtas> __host__ __device__ constexpr uint32_t tc_stage_bytes() { return (kTileM + TcCfg<kCtas>::kRRows) * kTileK * 2 * 2; }
+template <> struct TcCfg<1> { static constexpr int kStagesT = 4; static constexpr uint32_t kRRows = 256; };
+template <> struct TcCfg<2> { static constexpr int kStagesT = 6; static constexpr uint32_t kRRows = 128; };
+constexpr uint32_t kQTileBytes = kTileM * kTileK * 2;   // 16 KB
+template <int kCtas> __host__ __device__ constexpr uint32_t tc_stage_bytes() { return (kTileM + TcCfg<kCtas>::kRRows) * kTileK * 2; }
 template <int kCtas> __host__ __device__ constexpr size_t tc_smem_bytes() {
-  return TcCfg<kCtas>::kStagesT * tc_stage_bytes<kCtas>() + 1024 /*align*/ + 256 /*barriers*/ + (kTileN / 32) * 128 * 4;
+  return TcCfg<kCtas>::kStagesT * tc_stage_bytes<kCtas>() + 1024 /*align*/ + 256 /*barriers*/;
 }
 
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (-> even CTA)
@@ -241,8 +306,8 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // arrive on the
       ::"r"(bar), "h"((uint16_t)3)
       : "memory");
 }
-__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -257,29 +322,31 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// approximate d2 from the scaled fp16 inner product: ip = acc * inv_q * inv_r; cq = 2 inv_q
+__device__ __forceinline__ float make_d2_scaled(float qn, float rn, float acc, float cq, float inv_r) {
+  const float v = __fsub_rn(__fadd_rn(qn, rn), (acc * cq) * inv_r);
+  return v > 0.f ? v : 0.f;
+}
+
 template <int kCtas>
 __global__ void __launch_bounds__(kTcThreads, 1)
-knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_constant__ CUtensorMap map_qmid,
-                     const __grid_constant__ CUtensorMap map_rhi, const __grid_constant__ CUtensorMap map_rmid,
-                     const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int rows, int c0, int c1,
-                     int num_kb, int first_round, SelState sel) {
+knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
+                     const float4* __restrict__ rmeta, ErrModel em, int q_row0, int rows, int c0, int c1, int num_kb,
+                     int first_round, SelState sel) {
   constexpr int kSt = TcCfg<kCtas>::kStagesT;
   constexpr uint32_t kStageB = tc_stage_bytes<kCtas>();
-  constexpr uint32_t kRPlane = TcCfg<kCtas>::kRRows * kTileK * 2;   // bytes of one R plane tile in a stage
   constexpr int kPairM = kTileM * kCtas;                            // query rows per (pair) tile
-  // kind::f16 instruction descriptor: D=f32 (bit4), A=B=bf16 (bits 7,10), K-major both, N>>3 @17, M>>4 @24
-  constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
-                              ((uint32_t)(kPairM >> 4) << 24);
+  // kind::f16 instruction descriptor: D=f32 (bit4), A=B=f16 (format 0), K-major both, N>>3 @17, M>>4 @24
+  constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kPairM >> 4) << 24);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for SWIZZLE_128B tiles.  stage layout: [Qhi 16K][Qmid 16K][Rhi][Rmid]
+  // 1024-byte alignment for SWIZZLE_128B tiles.  stage layout: [Q 16K][R kRRows x 128 B]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSt * kStageB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  uint32_t* s_masks = reinterpret_cast<uint32_t*>(bars + 32);   // [kTileN/32][128] survivor bitmasks (epilogue)
-  const uint32_t bar_full = smem_u32(bars + 0);        // [kSt]  (pairs: only the leader's copies are used)
-  const uint32_t bar_empty = smem_u32(bars + 4);       // [kSt]
-  const uint32_t bar_tfull = smem_u32(bars + 8);       // [2] accumulator ready
-  const uint32_t bar_tempty = smem_u32(bars + 10);     // [2] accumulator drained (pairs: leader's copies)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const uint32_t bar_full = smem_u32(bars + 0);        // [kSt <= 8]  (pairs: only the leader's copies are used)
+  const uint32_t bar_empty = smem_u32(bars + 8);       // [kSt <= 8]
+  const uint32_t bar_tfull = smem_u32(bars + 16);      // [2] accumulator ready
+  const uint32_t bar_tempty = smem_u32(bars + 18);     // [2] accumulator drained (pairs: leader's copies)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t cta_rank = 0;
@@ -292,7 +359,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSt; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4 * kCtas); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8 * kCtas); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns = two 128x256 fp32 accumulators (per CTA)
@@ -312,8 +379,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
   if (warp == 0) {
     // ===== TMA producer (one thread per CTA) =====
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qhi) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rhi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
       uint32_t stage = 0, phase = 0;
       for (int t = worker; t < n_tiles; t += n_workers) {
         const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
@@ -325,16 +392,12 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
           const uint32_t fb = bar_full + 8 * stage;
           if (kCtas == 1) {
             mbar_arrive_expect_tx(fb, kStageB);
-            tma_load_2d(sbase, &map_qhi, fb, kb * kTileK, qy);
-            tma_load_2d(sbase + 16384, &map_qmid, fb, kb * kTileK, qy);
-            tma_load_2d(sbase + 32768, &map_rhi, fb, kb * kTileK, ry);
-            tma_load_2d(sbase + 32768 + kRPlane, &map_rmid, fb, kb * kTileK, ry);
+            tma_load_2d(sbase, &map_q, fb, kb * kTileK, qy);
+            tma_load_2d(sbase + kQTileBytes, &map_r, fb, kb * kTileK, ry);
           } else {
             if (leader) mbar_arrive_expect_tx(fb, 2 * kStageB);   // both CTAs' bytes land on the leader's barrier
-            tma_load_2d_pair(sbase, &map_qhi, fb, kb * kTileK, qy);
-            tma_load_2d_pair(sbase + 16384, &map_qmid, fb, kb * kTileK, qy);
-            tma_load_2d_pair(sbase + 32768, &map_rhi, fb, kb * kTileK, ry);
-            tma_load_2d_pair(sbase + 32768 + kRPlane, &map_rmid, fb, kb * kTileK, ry);
+            tma_load_2d_pair(sbase, &map_q, fb, kb * kTileK, qy);
+            tma_load_2d_pair(sbase + kQTileBytes, &map_r, fb, kb * kTileK, ry);
           }
           if (++stage == kSt) { stage = 0; phase ^= 1; }
         }
@@ -353,20 +416,12 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + stage * kStageB);
-          const uint64_t qhi = umma_desc_sw128(sbase), qmid = umma_desc_sw128(sbase + 16384);
-          const uint64_t rhi = umma_desc_sw128(sbase + 32768), rmid = umma_desc_sw128(sbase + 32768 + kRPlane);
+          const uint64_t qd = umma_desc_sw128(sbase), rd = umma_desc_sw128(sbase + kQTileBytes);
 #pragma unroll
           for (int kk = 0; kk < kTileK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 bf16 = 32 B along K inside the swizzle row
-            if (kCtas == 1) {
-              tc_mma_bf16(d_tmem, qhi + adv, rhi + adv, kIdesc, (kb | kk) != 0);
-              tc_mma_bf16(d_tmem, qhi + adv, rmid + adv, kIdesc, 1);
-              tc_mma_bf16(d_tmem, qmid + adv, rhi + adv, kIdesc, 1);
-            } else {
-              tc_mma_bf16_pair(d_tmem, qhi + adv, rhi + adv, kIdesc, (kb | kk) != 0);
-              tc_mma_bf16_pair(d_tmem, qhi + adv, rmid + adv, kIdesc, 1);
-              tc_mma_bf16_pair(d_tmem, qmid + adv, rhi + adv, kIdesc, 1);
-            }
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);  // 16 fp16 = 32 B along K inside the swizzle row
+            if (kCtas == 1) tc_mma_bf16(d_tmem, qd + adv, rd + adv, kIdesc, (kb | kk) != 0);
+            else tc_mma_f16_pair(d_tmem, qd + adv, rd + adv, kIdesc, (kb | kk) != 0);
           }
           // frees the smem stage (in both CTAs) when these MMAs retire
           if (kCtas == 1) tc_commit(bar_empty + 8 * stage); else tc_commit_pair(bar_empty + 8 * stage);
@@ -376,24 +431,37 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4); each CTA drains its own 128 rows =====
-    const int quarter = warp & 3;
+    // ===== epilogue warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; each CTA drains its own rows.
+    // One warp per scheduler cannot hide its own ALU / L1 latencies (r1 ncu: 27 instructions per score at IPC ~0.2
+    // left the single fp16 MMA pass waiting for the accumulator), hence two warps per quarter and a lean loop:
+    //   survive  <=>  (acc * 2 inv_q) * inv_r - ||r||^2 >= ||q||^2 - tau        (one LDG.128, FMUL, FFMA, FSETP, LOP)
+    // Survivor slots are claimed with ONE atomic per (row, 32-column chunk); the atomic's round trip is hidden behind
+    // the next chunk's TMEM load and tests, then the chunk's survivors are stored column by column, skipping (warp-
+    // uniformly) the columns in which no lane has one.
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    constexpr int kChunksPerWarp = kTileN / 32 / 2;
     uint32_t it = 0;
     for (int t = worker; t < n_tiles; t += n_workers, ++it) {
       const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
       const uint32_t buf = it & 1, use = it >> 1;
       const int row = rt * kPairM + (int)cta_rank * kTileM + quarter * 32 + lane;
       const bool row_ok = row < rows;
-      const float qnr = row_ok ? qn[q_row0 + row] : 0.f;
-      const float tau = row_ok ? sel.tau[row] : -1.f;
-      const int colbase = c0 + ct * kTileN;
+      float qnr = 0.f, cq = 0.f, thr = INFINITY;
+      if (row_ok) {
+        const float4 qm = em.qmeta[q_row0 + row];
+        qnr = qm.x;
+        cq = 2.f * qm.y;
+        // keep approx <= T + 2E (header comment); tau = +inf -> thr = -inf
+        thr = qnr - (sel.tau[row] + 2.f * row_err_bound(em, q_row0 + row));
+      }
+      const int colbase = c0 + ct * kTileN + half * (kTileN / 2);
       mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN + half * (kTileN / 2);
       if (first_round) {
         // round 0: tau = +inf, every score is a candidate -> dense store at (col - c0), no counters
 #pragma unroll 1
-        for (int c = 0; c < kTileN; c += 32) {
+        for (int c = 0; c < kTileN / 2; c += 32) {
           uint32_t v[32];
           tc_ld32(taddr + c, v);
           if (row_ok) {
@@ -403,74 +471,85 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int col = colbase + c + j;
+              float dd[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 rm = __ldg(rmeta + min(col + u, c1 - 1));
+                dd[u] = make_d2_scaled(qnr, rm.x, __uint_as_float(v[j + u]), cq, rm.y);
+              }
               if (col + 3 < c1) {
-                float4 d4;
-                d4.x = make_d2(qnr, __ldg(rn + col + 0), __uint_as_float(v[j + 0]));
-                d4.y = make_d2(qnr, __ldg(rn + col + 1), __uint_as_float(v[j + 1]));
-                d4.z = make_d2(qnr, __ldg(rn + col + 2), __uint_as_float(v[j + 2]));
-                d4.w = make_d2(qnr, __ldg(rn + col + 3), __uint_as_float(v[j + 3]));
-                *reinterpret_cast<float4*>(cd + j) = d4;
+                *reinterpret_cast<float4*>(cd + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
                 *reinterpret_cast<int4*>(ci + j) = make_int4(col, col + 1, col + 2, col + 3);
               } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (col + u < c1) {
-                    cd[j + u] = make_d2(qnr, __ldg(rn + col + u), __uint_as_float(v[j + u]));
-                    ci[j + u] = col + u;
-                  }
+                  if (col + u < c1) { cd[j + u] = dd[u]; ci[j + u] = col + u; }
               }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (kCtas == 1) mbar_arrive(bar_tempty + 8 * buf); else mbar_arrive_leader(bar_tempty + 8 * buf); }
       } else {
-        // pass 1: survivor bitmasks (no memory traffic); pass 2: ONE atomic slot claim per (row, tile), then
-        // re-read the accumulator chunks that hold survivors and store them.  (A per-survivor atomicAdd
-        // serialises ~700-cycle L2 round trips inside the warp and starves the MMA pipe: r1 ncu capture.)
-        uint32_t* masks = s_masks + (threadIdx.x - 64);    // [cc * 128 + epilogue thread]
-        int nsurv = 0;
-#pragma unroll 1
-        for (int cc = 0; cc < kTileN / 32; ++cc) {
-          uint32_t v[32];
-          tc_ld32(taddr + cc * 32, v);
+        float* cd = sel.cand_d2 + (size_t)row * kCandCap;
+        int* ci = sel.cand_idx + (size_t)row * kCandCap;
+        auto test_chunk = [&](const uint32_t (&v)[32], int col0) -> uint32_t {
           uint32_t m = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = colbase + cc * 32 + j;
-            const float d2 = make_d2(qnr, __ldg(rn + min(col, c1 - 1)), __uint_as_float(v[j]));
-            if (col < c1 && d2 <= tau) m |= 1u << j;
-          }
-          m = row_ok ? m : 0u;
-          masks[cc * 128] = m;
-          nsurv += __popc(m);
-        }
-        int pos = 0;
-        if (nsurv) {
-          pos = atomicAdd(sel.cnt + row, nsurv);
-          if (pos + nsurv > kCandCap) *sel.overflow = 1;
-        }
-#pragma unroll 1
-        for (int cc = 0; cc < kTileN / 32; ++cc) {
-          const uint32_t m = masks[cc * 128];
-          if (__any_sync(0xffffffffu, m != 0u)) {   // tcgen05.ld is warp-collective
-            uint32_t v[32];
-            tc_ld32(taddr + cc * 32, v);
+          if (col0 + 32 <= c1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
+              const float4 rm = __ldg(rmeta + col0 + j);
+              if (fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x) >= thr) m |= 1u << j;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float4 rm = __ldg(rmeta + min(col0 + j, c1 - 1));
+              if (col0 + j < c1 && fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x) >= thr) m |= 1u << j;
+            }
+          }
+          return m;
+        };
+        auto store_chunk = [&](const uint32_t (&v)[32], uint32_t m, int pos, int col0) {
+          const uint32_t any = __reduce_or_sync(0xffffffffu, m);
+          if (any == 0u) return;
+          if (m != 0u && pos + __popc(m) > kCandCap) *sel.overflow = 1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if ((any >> j) & 1u) {            // warp-uniform skip of columns without survivors
               if ((m >> j) & 1u) {
-                const int col = colbase + cc * 32 + j;
                 if (pos < kCandCap) {
-                  sel.cand_d2[(size_t)row * kCandCap + pos] = make_d2(qnr, __ldg(rn + col), __uint_as_float(v[j]));
-                  sel.cand_idx[(size_t)row * kCandCap + pos] = col;
+                  const float4 rm = __ldg(rmeta + col0 + j);
+                  cd[pos] = make_d2_scaled(qnr, rm.x, __uint_as_float(v[j]), cq, rm.y);
+                  ci[pos] = col0 + j;
                 }
                 ++pos;
               }
             }
           }
+        };
+        uint32_t va[32], vb[32];
+        uint32_t ma = 0, mb = 0;
+        int pa = 0, pb = 0;
+#pragma unroll 1
+        for (int cc = 0; cc < kChunksPerWarp; cc += 2) {
+          tc_ld32(taddr + cc * 32, va);
+          ma = test_chunk(va, colbase + cc * 32);
+          if (ma) pa = atomicAdd(sel.cnt + row, __popc(ma));
+          if (cc > 0) store_chunk(vb, mb, pb, colbase + (cc - 1) * 32);
+          tc_ld32(taddr + (cc + 1) * 32, vb);
+          if (cc + 2 >= kChunksPerWarp) {     // last TMEM read of this tile: hand the accumulator back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (kCtas == 1) mbar_arrive(bar_tempty + 8 * buf); else mbar_arrive_leader(bar_tempty + 8 * buf); }
+          }
+          mb = test_chunk(vb, colbase + (cc + 1) * 32);
+          if (mb) pb = atomicAdd(sel.cnt + row, __popc(mb));
+          store_chunk(va, ma, pa, colbase + cc * 32);
         }
+        store_chunk(vb, mb, pb, colbase + (kChunksPerWarp - 1) * 32);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (kCtas == 1) mbar_arrive(bar_tempty + 8 * buf); else mbar_arrive_leader(bar_tempty + 8 * buf); }
     }
   }
   tc_fence_before();
@@ -483,14 +562,17 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_qhi, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-row candidate refinement (one CTA per row).
-// Non-final: radix-select the k-th smallest d2 (3 passes of 11/11/10 bits over the fp32 bit pattern; d2 >= +0
-// so unsigned order == float order), keep every candidate with d2 <= T (>= k of them; exact ties at T are all
-// kept), tau = T.  Final: the same selection, then a bitonic sort of the ~k survivors on the 64-bit key
-// (d2 bits << 32 | idx) => ascending (d2, idx), and the first k are written out (global row = offset + idx).
+// Per-row candidate refinement (one CTA per row).  Radix-select the k-th smallest d2 T (3 passes of 11/11/10 bits over
+// the fp32 bit pattern; d2 >= +0 so unsigned order == float order), then by mode:
+//   kRefineSelect : approximate scores.  Keep every candidate with d2 <= T + 2E (header comment), tau = T.
+//   kRefineFinal  : exact (re-scored) values.  Keep d2 <= T, bitonic sort of the survivors on the 64-bit key
+//                   (d2 bits << 32 | idx) => ascending (d2, idx); the first k are written out (global row = offset + idx).
+//   kRefineExactK : exact values, conservative schedule.  Same sort, the first k go back to the candidate list
+//                   (count = k exactly, ties broken by index like the final order), tau = T.
+enum { kRefineSelect = 0, kRefineFinal = 1, kRefineExactK = 2 };
 __global__ void __launch_bounds__(256)
-knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int q_row0, float* __restrict__ d2_out,
-                  long long* __restrict__ idx_out) {
+knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, long long row_offset, int q_row0,
+                  float* __restrict__ d2_out, long long* __restrict__ idx_out) {
   __shared__ __align__(16) unsigned s_v[kCandCap];   // d2 bit patterns   } re-used as 64-bit sort keys
   __shared__ __align__(16) int s_i[kCandCap];        // candidate rows    } in the final pass
   __shared__ int s_hist[2048];
@@ -499,7 +581,7 @@ knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   int n = sel.cnt[row];
   if (n > kCandCap) n = kCandCap;
-  if (!final_pass && n <= k) return;
+  if (mode != kRefineFinal && n <= k) return;
   float* cd = sel.cand_d2 + (size_t)row * kCandCap;
   int* ci = sel.cand_idx + (size_t)row * kCandCap;
   for (int i = tid; i < n; i += 256) { s_v[i] = __float_as_uint(cd[i]); s_i[i] = ci[i]; }
@@ -545,11 +627,15 @@ knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int
       __syncthreads();
     }
     const unsigned T = prefix;
+    // approximate scores: everything within 2E of the k-th best may still belong to the exact top k
+    const unsigned keepT = mode == kRefineSelect
+                               ? __float_as_uint(__fadd_ru(__uint_as_float(T), 2.f * row_err_bound(em, q_row0 + row)))
+                               : T;
     if (tid == 0) s_out = 0;
     __syncthreads();
     for (int i = tid; i < n; i += 256) {
       const unsigned v = s_v[i];
-      if (v <= T) {
+      if (v <= keepT) {
         const int pos = atomicAdd(&s_out, 1);
         cd[pos] = __uint_as_float(v);
         ci[pos] = s_i[i];
@@ -559,8 +645,8 @@ knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int
     c = s_out;
     if (tid == 0) { sel.cnt[row] = c; sel.tau[row] = __uint_as_float(T); }
   }
-  if (!final_pass) return;
-  // final: sort the c (~k) survivors by (d2, idx)
+  if (mode == kRefineSelect) return;
+  // sort the c (~k) survivors by (d2, idx)
   __syncthreads();
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_v);   // s_v and s_i are contiguous: 32 KB
   static_assert(sizeof(unsigned) * kCandCap * 2 == sizeof(unsigned long long) * kCandCap, "key aliasing");
@@ -591,6 +677,15 @@ knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int
       __syncthreads();
     }
   }
+  if (mode == kRefineExactK) {
+    const int keep = c < k ? c : k;
+    for (int i = tid; i < keep; i += 256) {
+      cd[i] = __uint_as_float((unsigned)(keys[i] >> 32));
+      ci[i] = (int)(unsigned)keys[i];
+    }
+    if (tid == 0) sel.cnt[row] = keep;
+    return;
+  }
   const size_t o = (size_t)(q_row0 + row) * k;
   for (int i = tid; i < k; i += 256) {
     if (i < c) {
@@ -603,11 +698,10 @@ knn_refine_kernel(SelState sel, int k, int final_pass, long long row_offset, int
   }
 }
 
-// Exact re-scoring of the selected candidates: the tensor-core inner products carry the accumulation
-// error of the fp32 TMEM accumulator chain (measured ~1e-5 abs on d2 at D=1536, growing with D), which is
-// enough to order near-ties differently from an fp32 evaluation.  The <= k+margin survivors of each row are
-// re-evaluated with plain fp32 FMAs on the resident fp32 rows (one warp per candidate, lanes stride the
-// channels in float4, shuffle-tree reduction), then the final sort uses these values.
+// Exact re-scoring of the surviving candidates: the single fp16 pass only has to be good enough to discard (its error
+// is bounded, see the header); the <= k + few survivors of each row are re-evaluated with plain fp32 FMAs on the
+// resident fp32 rows (one warp per candidate, lanes stride the channels in float4, shuffle-tree reduction), and the
+// final selection + sort uses these values.
 __global__ void __launch_bounds__(256)
 knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __restrict__ r32,
                    const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int D) {
@@ -684,6 +778,16 @@ merge_topk_kernel(const float* __restrict__ d2p, const long long* __restrict__ i
   }
 }
 
+// test hook: dense approximate scores of round 0 + the row's error bound
+__global__ void knn_debug_copy_kernel(SelState sel, ErrModel em, int q_row0, int rows, int Nr, float* __restrict__ approx_out,
+                                      float* __restrict__ bound_out) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  for (int j = threadIdx.x; j < Nr; j += blockDim.x)
+    approx_out[(size_t)(q_row0 + row) * Nr + j] = sel.cand_d2[(size_t)row * kCandCap + j];
+  if (threadIdx.x == 0) bound_out[q_row0 + row] = row_err_bound(em, q_row0 + row);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 struct KnnLayout {
@@ -719,14 +823,14 @@ static KnnLayout carve_knn(void* ws, int Nq, int Nr) {
   return L;
 }
 
-static int make_map(CUtensorMap* m, const __nv_bfloat16* base, int n, int Dp, int box_rows) {
+static int make_map(CUtensorMap* m, const __half* base, int n, int Dp, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SEGVLAD_ECUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)n};
   cuuint64_t strides[1] = {(cuuint64_t)Dp * 2};
   cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box, estr,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SEGVLAD_ECUDA; }
@@ -745,12 +849,12 @@ static int next_chunk(int seen, int k, int Nr, bool safe) {
   return (int)c;
 }
 
-struct TcArgs { BankView q, r; CUtensorMap mqhi, mqmid, mrhi, mrmid; int num_sms; int ctas; };
+struct TcArgs { BankView q, r; CUtensorMap mq, mr; int num_sms; int ctas; };
 struct SimtArgs { const float* q; const float* r; };
 
 // Host-streamed reference bank: fp32 rows arrive from pinned host memory on a copy stream, sub-chunk by
 // sub-chunk, directly into the bank's fp32 region; the compute stream waits for each sub-chunk's event, splits it
-// into bf16 planes and scans it while the next sub-chunks are still in flight over PCIe.
+// into the fp16 plane and scans it while the next sub-chunks are still in flight over PCIe.
 struct HostFeed {
   const float* r_host;     // [Nr, D] pinned host rows
   cudaStream_t copy;       // copy stream
@@ -762,16 +866,16 @@ struct BlockCtx { SelState sel; const float* qn; const float* rn; };
 static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockCtx& L, int q_row0, int rows, int Nr,
                      int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
                      cudaStream_t st, const HostFeed* feed = nullptr) {
-  // tensor-core path: select k + margin by the approximate distances, re-score those exactly, keep k
-  const int ksel = tc ? (k + kRescoreMargin) : k;
-  const int first = next_chunk(0, ksel, Nr, safe);
+  // tensor-core path: filter on the approximate distances with the error-model margin, re-score exactly, keep k
+  const ErrModel em = tc ? ErrModel{ta->q.meta, ta->r.stats, acc_err_const(D)} : ErrModel{nullptr, nullptr, 0.f};
+  const int first = next_chunk(0, k, Nr, safe);
   sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, first);
   SV_CHECK_LAUNCH();
   // schedule: rounds (refine boundaries) split into sub-chunks (one filter launch each)
   SubChunk sched[512];
   int ns = 0;
   for (int seen = 0; seen < Nr;) {
-    const int chunk = next_chunk(seen, ksel, Nr, safe);
+    const int chunk = next_chunk(seen, k, Nr, safe);
     const int sub = (feed && seen > 0) ? feed->sub_rows : chunk;
     for (int s0 = seen; s0 < seen + chunk; s0 += sub) {
       SV_REQUIRE(ns < 512, "knn: schedule too long");
@@ -794,10 +898,7 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     const int c0 = sched[i].c0, c1 = sched[i].c1, chunk = c1 - c0, first_round = sched[i].first_round;
     if (feed) {
       SV_CHECK_CUDA(cudaStreamWaitEvent(st, ev[i], 0));
-      bank_prepare_rows_kernel<<<(chunk + 7) / 8, 256, 0, st>>>(ta->r.x32, c0, chunk, D, ta->r.Dp,
-                                                                const_cast<__nv_bfloat16*>(ta->r.hi),
-                                                                const_cast<__nv_bfloat16*>(ta->r.mid),
-                                                                const_cast<float*>(ta->r.norms));
+      bank_prepare_rows_kernel<<<(chunk + 7) / 8, 256, 0, st>>>(c0, chunk, D, bank_out(ta->r));
       SV_CHECK_LAUNCH();
     }
     const int pslot = prof_begin(SEGVLAD_PROF_KNN_FILTER, st);
@@ -815,15 +916,13 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<2>, ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid,
-                                         ta->q.norms, ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK, first_round,
-                                         L.sel));
+        SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<2>, ta->mq, ta->mr, ta->r.meta, em, q_row0, rows, c0,
+                                         c1, ta->q.Dp / kTileK, first_round, L.sel));
       } else {
         const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
         const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
         knn_tc_filter_kernel<1><<<grid, kTcThreads, tc_smem_bytes<1>(), st>>>(
-            ta->mqhi, ta->mqmid, ta->mrhi, ta->mrmid, ta->q.norms, ta->r.norms, q_row0, rows, c0, c1, ta->q.Dp / kTileK,
-            first_round, L.sel);
+            ta->mq, ta->mr, ta->r.meta, em, q_row0, rows, c0, c1, ta->q.Dp / kTileK, first_round, L.sel);
       }
     } else {
       dim3 grid((chunk + 63) / 64, (rows + 63) / 64);
@@ -833,17 +932,19 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     prof_end(pslot, st);
     SV_CHECK_LAUNCH();
     if (!sched[i].last_of_round) continue;
-    const int final_pass = sched[i].final_pass;
-    if (final_pass && tc) {
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, ksel, 0, row_offset, q_row0, d2_out, idx_out);
+    const bool final_pass = sched[i].final_pass != 0;
+    if (tc && !safe && final_pass) {   // last approximate selection before the exact re-score
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
+    }
+    if (tc && (safe || final_pass)) {
       const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
       knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D);
       prof_end(rslot, st);
       SV_CHECK_LAUNCH();
     }
-    knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, final_pass ? k : ksel, final_pass, row_offset, q_row0, d2_out,
-                                            idx_out);
+    const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : kRefineSelect);
+    knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, row_offset, q_row0, d2_out, idx_out);
     SV_CHECK_LAUNCH();
   }
   if (feed)
@@ -870,7 +971,8 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
       const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
       sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel[0], rows, 0);
       SV_CHECK_LAUNCH();
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel[0], k, 1, row_offset, q0, d2_out, idx_out);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel[0], ErrModel{nullptr, nullptr, 0.f}, k, kRefineFinal, row_offset, q0,
+                                              d2_out, idx_out);
       SV_CHECK_LAUNCH();
     }
     return SEGVLAD_OK;
@@ -934,9 +1036,10 @@ extern "C" size_t segvlad_bank_bytes(int n, int D) {
   if (n < 0 || D <= 0) return 0;
   Carver c(nullptr);
   const int Dp = padded_dim(D);
-  c.take<__nv_bfloat16>((size_t)n * Dp);
-  c.take<__nv_bfloat16>((size_t)n * Dp);
+  c.take<__half>((size_t)n * Dp);
   c.take<float>(n);
+  c.take<float4>(n);
+  c.take<unsigned>(64);
   c.take<float>((size_t)n * D);
   return c.total() + 256;
 }
@@ -946,10 +1049,9 @@ extern "C" int segvlad_bank_prepare(const float* x, int n, int D, void* bank, vo
   SV_REQUIRE(n >= 0 && D > 0 && bank, "bank_prepare: bad arguments");
   SV_REQUIRE((reinterpret_cast<uintptr_t>(bank) & 255) == 0, "bank_prepare: bank must be 256-byte aligned");
   if (n == 0) return SEGVLAD_OK;
-  BankView v = bank_view(bank, n, D);
-  bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, v.Dp, const_cast<__nv_bfloat16*>(v.hi),
-                                                   const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms),
-                                                   const_cast<float*>(v.x32));
+  BankOut b = bank_out(bank_view(bank, n, D));
+  SV_CHECK_CUDA(cudaMemsetAsync(b.stats, 0, 64 * sizeof(unsigned), st));
+  bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, b);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }
@@ -959,10 +1061,9 @@ extern "C" int segvlad_bank_prepare_f64(const double* x, int n, int D, int norma
   SV_REQUIRE(n >= 0 && D > 0 && bank, "bank_prepare_f64: bad arguments");
   SV_REQUIRE((reinterpret_cast<uintptr_t>(bank) & 255) == 0, "bank_prepare_f64: bank must be 256-byte aligned");
   if (n == 0) return SEGVLAD_OK;
-  BankView v = bank_view(bank, n, D);
-  bank_prepare_f64_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, v.Dp, normalize_rows, const_cast<__nv_bfloat16*>(v.hi),
-                                                       const_cast<__nv_bfloat16*>(v.mid), const_cast<float*>(v.norms),
-                                                       const_cast<float*>(v.x32));
+  BankOut b = bank_out(bank_view(bank, n, D));
+  SV_CHECK_CUDA(cudaMemsetAsync(b.stats, 0, 64 * sizeof(unsigned), st));
+  bank_prepare_f64_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, normalize_rows, b);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }
@@ -980,10 +1081,8 @@ static int tc_setup(TcArgs& ta, const void* qbank, int Nq, const void* rbank, in
   const char* env = getenv("SEGVLAD_KNN_CTAS");      // 2 (default): CTA pairs / cta_group::2; 1: single-CTA tiles
   ta.ctas = (env && env[0] == '1') ? 1 : 2;
   const int r_box = ta.ctas == 2 ? kTileN / 2 : kTileN;
-  if ((rc = make_map(&ta.mqhi, ta.q.hi, Nq, ta.q.Dp, kTileM))) return rc;
-  if ((rc = make_map(&ta.mqmid, ta.q.mid, Nq, ta.q.Dp, kTileM))) return rc;
-  if ((rc = make_map(&ta.mrhi, ta.r.hi, Nr, ta.r.Dp, r_box))) return rc;
-  if ((rc = make_map(&ta.mrmid, ta.r.mid, Nr, ta.r.Dp, r_box))) return rc;
+  if ((rc = make_map(&ta.mq, ta.q.h16, Nq, ta.q.Dp, kTileM))) return rc;
+  if ((rc = make_map(&ta.mr, ta.r.h16, Nr, ta.r.Dp, r_box))) return rc;
   int dev = 0;
   SV_CHECK_CUDA(cudaGetDevice(&dev));
   SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1033,8 +1132,9 @@ extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r
                                 cudaMemcpyHostToDevice, cp));
   SV_CHECK_CUDA(cudaEventRecord(eq, cp));
   SV_CHECK_CUDA(cudaStreamWaitEvent(st, eq, 0));
-  bank_prepare_rows_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(ta.q.x32, 0, Nq, D, ta.q.Dp, const_cast<__nv_bfloat16*>(ta.q.hi),
-                                                        const_cast<__nv_bfloat16*>(ta.q.mid), const_cast<float*>(ta.q.norms));
+  SV_CHECK_CUDA(cudaMemsetAsync(const_cast<unsigned*>(ta.q.stats), 0, 64 * sizeof(unsigned), st));
+  SV_CHECK_CUDA(cudaMemsetAsync(const_cast<unsigned*>(ta.r.stats), 0, 64 * sizeof(unsigned), st));
+  bank_prepare_rows_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(0, Nq, D, bank_out(ta.q));
   SV_CHECK_LAUNCH();
   HostFeed feed{r_host, cp, 16384};
   rc = knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out), workspace,
@@ -1042,6 +1142,51 @@ extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r
   cudaEventDestroy(e0);
   cudaEventDestroy(eq);
   return rc;
+}
+
+extern "C" int segvlad_knn_debug_approx(const void* qbank, int Nq, const void* rbank, int Nr, int D, float* approx_out,
+                                        float* bound_out, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(D > 0 && Nq > 0 && Nr > 0 && Nr <= kCandCap, "knn_debug_approx: need 0 < Nr <= %d", kCandCap);
+  TcArgs ta;
+  int rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
+  if (rc) return rc;
+  KnnLayout L = carve_knn(workspace, Nq, Nr);
+  if (!workspace || workspace_bytes < L.total) {
+    set_error("knn_debug_approx: workspace %zu < required %zu", workspace_bytes, L.total);
+    return SEGVLAD_EWORKSPACE;
+  }
+  const ErrModel em{ta.q.meta, ta.r.stats, acc_err_const(D)};
+  for (int q0 = 0; q0 < Nq; q0 += L.block_rows) {
+    const int rows = (Nq - q0) < L.block_rows ? (Nq - q0) : L.block_rows;
+    sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel[0], rows, Nr);
+    SV_CHECK_LAUNCH();
+    if (ta.ctas == 2) {
+      const int n_tiles = ((rows + 2 * kTileM - 1) / (2 * kTileM)) * ((Nr + kTileN - 1) / kTileN);
+      int pairs = ta.num_sms / 2;
+      if (n_tiles < pairs) pairs = n_tiles;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * pairs);
+      cfg.blockDim = dim3(kTcThreads);
+      cfg.dynamicSmemBytes = tc_smem_bytes<2>();
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<2>, ta.mq, ta.mr, ta.r.meta, em, q0, rows, 0, Nr,
+                                       ta.q.Dp / kTileK, 1, L.sel[0]));
+    } else {
+      const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((Nr + kTileN - 1) / kTileN);
+      const int grid = n_tiles < ta.num_sms ? n_tiles : ta.num_sms;
+      knn_tc_filter_kernel<1><<<grid, kTcThreads, tc_smem_bytes<1>(), st>>>(ta.mq, ta.mr, ta.r.meta, em, q0, rows, 0, Nr,
+                                                                          ta.q.Dp / kTileK, 1, L.sel[0]);
+    }
+    SV_CHECK_LAUNCH();
+    knn_debug_copy_kernel<<<rows, 256, 0, st>>>(L.sel[0], em, q0, rows, Nr, approx_out, bound_out);
+    SV_CHECK_LAUNCH();
+  }
+  return SEGVLAD_OK;
 }
 
 extern "C" int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, int64_t row_offset, int D, int k,

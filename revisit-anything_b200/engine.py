@@ -143,7 +143,8 @@ def aggregate_residuals(residuals: torch.Tensor, labels: torch.Tensor, N: int, D
 # --------------------------------------------------------------------------------------------
 @dataclass
 class Bank:
-    """Kernel-ready resident form of an [n, D] descriptor matrix (bf16 hi/mid planes + norms)."""
+    """Kernel-ready resident form of an [n, D] descriptor matrix (scaled fp16 plane, norms / scan error bounds,
+    fp32 rows for the exact re-score)."""
     buf: torch.Tensor
     n: int
     D: int
@@ -170,7 +171,7 @@ class Bank:
 
 
 def knn(q: Bank, r: Bank, k: int, row_offset: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """tcgen05 all-pairs squared-L2 + fused threshold filter + top-k.  Returns (d2 [Nq,k] fp32 ascending,
+    """tcgen05 all-pairs squared-L2 (one fp16 pass, error-bounded filter, exact fp32 re-score) + top-k.  Returns (d2 [Nq,k] fp32 ascending,
     idx [Nq,k] int64 global rows; (+inf,-1) padded)."""
     assert q.D == r.D
     dev = q.buf.device
@@ -200,6 +201,19 @@ def knn_from_host(q_host: torch.Tensor, r_host: torch.Tensor, k: int, row_offset
                                       int(row_offset), D, k, _ptr(qb.buf), _ptr(rb.buf), _ptr(d2), _ptr(idx), _ptr(ws),
                                       ws.numel(), _stream(), None), "segvlad_knn_from_host")
     return d2, idx, qb, rb
+
+
+def knn_debug_approx(q: Bank, r: Bank) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Test hook (r.n <= 4096): the tensor-core pass's approximate d2 for every pair [Nq, Nr] and the per-query
+    error bound [Nq] the filter assumes on |approx - fp32 value|."""
+    assert q.D == r.D
+    dev = q.buf.device
+    approx = torch.empty((q.n, r.n), dtype=torch.float32, device=dev)
+    bound = torch.empty((q.n,), dtype=torch.float32, device=dev)
+    ws = _ws(lib().segvlad_knn_workspace_bytes(q.n, r.n, q.D, 1), dev)
+    check(lib().segvlad_knn_debug_approx(_ptr(q.buf), q.n, _ptr(r.buf), r.n, q.D, _ptr(approx), _ptr(bound), _ptr(ws),
+                                         ws.numel(), _stream()), "segvlad_knn_debug_approx")
+    return approx, bound
 
 
 def knn_simt(q: torch.Tensor, r: torch.Tensor, k: int, row_offset: int = 0):

@@ -141,3 +141,76 @@ def test_knn_from_host_streamed_matches_resident():
     # pageable (non-pinned) host memory also works (no overlap, same answer)
     d2p, idxp, _, _ = engine.knn_from_host(q.cpu(), r.cpu(), 200, row_offset=77)
     np.testing.assert_array_equal(idxp.cpu().numpy(), idx_res)
+
+
+def _exact_d2_fp64(q, r):
+    q64, r64 = q.double(), r.double()
+    d = (q64 * q64).sum(1)[:, None] + (r64 * r64).sum(1)[None, :] - 2.0 * (q64 @ r64.T)
+    return d.clamp_min(0.0)
+
+
+@pytest.mark.parametrize("D", [64, 520, 1536, 4096])
+@pytest.mark.parametrize("kind", ["unit", "huge", "tiny", "mixed_rows", "heavy_tail", "near_duplicates"])
+def test_error_model_bounds_the_fp16_pass(D, kind):
+    """The filter is exact only if |approximate d2 - fp32 d2| <= E_row for EVERY pair (knn.cu header): check the bound
+    the library assumes against fp64 on all pairs of a 512 x 4096 problem, for inputs that stress the fp16 plane."""
+    g = torch.Generator(device=DEV).manual_seed(D + len(kind))
+    Nq, Nr = 512, 4096
+    q = torch.randn(Nq, D, generator=g, device=DEV)
+    r = torch.randn(Nr, D, generator=g, device=DEV)
+    if kind == "unit":
+        q, r = torch.nn.functional.normalize(q, dim=1), torch.nn.functional.normalize(r, dim=1)
+    elif kind == "huge":
+        q, r = q * 3.0e5, r * 7.0e5                      # far outside the fp16 range without the row scaling
+    elif kind == "tiny":
+        q, r = q * 1.0e-9, r * 3.0e-10
+    elif kind == "mixed_rows":
+        q = q * torch.logspace(-4, 4, Nq, device=DEV)[:, None]
+        r = r * torch.logspace(-3, 3, Nr, device=DEV)[torch.randperm(Nr, generator=g, device=DEV)][:, None]
+    elif kind == "heavy_tail":                            # a few huge channels: most of the row falls into the low fp16 bits
+        q = q * torch.exp(3.0 * torch.randn(Nq, D, generator=g, device=DEV))
+        r = r * torch.exp(3.0 * torch.randn(Nr, D, generator=g, device=DEV))
+    else:                                                 # d2 ~ 0 by cancellation
+        base = torch.nn.functional.normalize(torch.randn(8, D, generator=g, device=DEV), dim=1)
+        q = base[torch.arange(Nq, device=DEV) % 8] + 1e-3 * q / D ** 0.5
+        r = base[torch.arange(Nr, device=DEV) % 8] + 1e-3 * r / D ** 0.5
+    q, r = q.contiguous(), r.contiguous()
+    approx, bound = engine.knn_debug_approx(engine.Bank.prepare(q), engine.Bank.prepare(r))
+    torch.cuda.synchronize()
+    exact = _exact_d2_fp64(q, r)
+    err = (approx.double() - exact).abs()
+    ratio = (err / bound.double()[:, None]).max().item()
+    assert torch.isfinite(bound).all() and (bound > 0).all()
+    assert ratio <= 1.0, f"approximate score off by {ratio:.3f} x the assumed bound"
+    # the bound must also be useful: for unit-norm rows a small fraction of the d2 spread (~ 2 / sqrt(D))
+    if kind == "unit":
+        assert bound.max().item() < 0.05 * 2.0 / D ** 0.5 + 1e-3
+
+
+@pytest.mark.parametrize("runner", [_run_simt, _run_tc], ids=["simt", "tcgen05"])
+def test_massive_duplicates_select_by_index(runner):
+    # 6000 identical rows: every candidate buffer overflows under the optimistic schedule and the approximate scores
+    # cannot separate them; the conservative schedule must return the k smallest INDICES of the tie group
+    q, r = synth.make_descriptor_bank(200, 20000, 128, seed=21, planted=0, device=DEV)
+    dup = torch.randperm(20000, generator=torch.Generator().manual_seed(1))[:6000].to(DEV)
+    r[dup] = q[7]
+    d2, idx = runner(q, r, 200)
+    want = np.sort(dup.cpu().numpy())[:200]
+    np.testing.assert_array_equal(idx[7], want)
+    assert (d2[7] <= 2e-6).all()
+    d64, i64 = _ref(q, r, 208)
+    rows = [i for i in range(200) if i != 7]
+    np.testing.assert_allclose(d2[rows], d64[rows, :200], rtol=1e-5, atol=2e-6)
+
+
+def test_unnormalised_rows_of_mixed_magnitude():
+    # faiss.IndexFlatL2 takes arbitrary fp32 rows: per-row power-of-two scaling keeps the fp16 plane in range
+    g = torch.Generator(device=DEV).manual_seed(33)
+    q = torch.randn(300, 256, generator=g, device=DEV) * torch.logspace(-2, 2, 300, device=DEV)[:, None]
+    r = torch.randn(20000, 256, generator=g, device=DEV) * torch.logspace(-2, 2, 20000, device=DEV)[
+        torch.randperm(20000, generator=g, device=DEV)][:, None]
+    d2, idx = _run_tc(q.contiguous(), r.contiguous(), 100)
+    d2s, idxs = _run_simt(q.contiguous(), r.contiguous(), 100)
+    d64, i64 = _ref(q, r, 100)
+    np.testing.assert_allclose(d2, d64, rtol=2e-5)
+    assert (idx == i64).mean() > 0.999 and (idx == idxs).mean() > 0.999
