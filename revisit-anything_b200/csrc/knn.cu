@@ -40,6 +40,7 @@ namespace segvlad {
 
 constexpr int kCandCap = 4096;     // candidate slots per query row
 constexpr int kMaxK = 1024;
+constexpr int kExactFlag = (int)0x80000000;  // cand_idx sign bit: this candidate's d2 is already the exact fp32 value
 constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
 constexpr int kTcThreads = 320;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quarter)
@@ -656,7 +657,7 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, long long row_offs
 #pragma unroll
   for (int t = 0; t < kCandCap / 256; ++t) {
     const int i = tid + t * 256;
-    mykeys[t] = (i < c) ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | (unsigned)ci[i]) : ~0ull;
+    mykeys[t] = (i < c) ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | (unsigned)(ci[i] & ~kExactFlag)) : ~0ull;
   }
   __syncthreads();   // everyone has read cd/ci (global) before the smem region is re-purposed
 #pragma unroll
@@ -681,7 +682,7 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, long long row_offs
     const int keep = c < k ? c : k;
     for (int i = tid; i < keep; i += 256) {
       cd[i] = __uint_as_float((unsigned)(keys[i] >> 32));
-      ci[i] = (int)(unsigned)keys[i];
+      ci[i] = (int)(unsigned)keys[i] | kExactFlag;
     }
     if (tid == 0) sel.cnt[row] = keep;
     return;
@@ -711,10 +712,11 @@ knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __r
   const float* qr = q32 + (size_t)(q_row0 + row) * D;
   const float qnr = qn[q_row0 + row];
   float* cd = sel.cand_d2 + (size_t)row * kCandCap;
-  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  int* ci = sel.cand_idx + (size_t)row * kCandCap;
   const bool vec = (D & 3) == 0;
   for (int j = w; j < n; j += 8) {
     const int col = ci[j];
+    if (col < 0) continue;   // already exact (kept by an earlier exact selection)
     const float* rr = r32 + (size_t)col * D;
     float acc = 0.f;
     if (vec) {
@@ -728,7 +730,7 @@ knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __r
       for (int d = lane; d < D; d += 32) acc = fmaf(__ldg(qr + d), __ldg(rr + d), acc);
     }
     acc = warp_sum(acc);
-    if (lane == 0) cd[j] = make_d2(qnr, rn[col], acc);
+    if (lane == 0) { cd[j] = make_d2(qnr, rn[col], acc); ci[j] = col | kExactFlag; }
   }
 }
 
@@ -837,12 +839,23 @@ static int make_map(CUtensorMap* m, const __half* base, int n, int Dp, int box_r
   return SEGVLAD_OK;
 }
 
-// chunk schedule: first chunk fills the buffer, later chunks grow with the number of refs already seen
+// chunk schedule: first chunk fills the buffer, later chunks grow with the number of refs already seen; a chunk is
+// sized to leave ~ (C - k) / fill survivors per row (fill = head-room against uneven banks AND the knob that trades
+// survivor stores in the filter epilogue against the number of refine rounds)
+static double fill_factor() {
+  static double f = 0.0;
+  if (f == 0.0) {
+    const char* e = getenv("SEGVLAD_KNN_FILL");
+    f = e ? atof(e) : 2.5;
+    if (!(f >= 1.5)) f = 1.5;
+  }
+  return f;
+}
 static int next_chunk(int seen, int k, int Nr, bool safe) {
   long long c;
   if (seen == 0) c = kCandCap;
   else if (safe) c = kCandCap - k;
-  else c = (long long)((double)seen * (double)(kCandCap - k) / ((double)k * 2.5));
+  else c = (long long)((double)seen * (double)(kCandCap - k) / ((double)k * fill_factor()));
   c = c / kTileN * kTileN;
   if (c < kTileN) c = kTileN;
   if (c > Nr - seen) c = Nr - seen;
@@ -868,6 +881,10 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
                      cudaStream_t st, const HostFeed* feed = nullptr) {
   // tensor-core path: filter on the approximate distances with the error-model margin, re-score exactly, keep k
   const ErrModel em = tc ? ErrModel{ta->q.meta, ta->r.stats, acc_err_const(D)} : ErrModel{nullptr, nullptr, 0.f};
+  // Host-streamed bank: the GPU waits for PCIe anyway, so every sub-chunk is closed with an exact selection (select ->
+  // re-score only the new survivors -> exact k); when the last rows arrive only their few survivors are left to
+  // re-score, instead of all k + margin candidates of every query.
+  const bool incremental = tc && feed != nullptr && !safe;
   const int first = next_chunk(0, k, Nr, safe);
   sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, first);
   SV_CHECK_LAUNCH();
@@ -880,7 +897,7 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     for (int s0 = seen; s0 < seen + chunk; s0 += sub) {
       SV_REQUIRE(ns < 512, "knn: schedule too long");
       const int s1 = (s0 + sub < seen + chunk) ? s0 + sub : seen + chunk;
-      sched[ns++] = {s0, s1, seen == 0, s1 == seen + chunk, s1 == Nr};
+      sched[ns++] = {s0, s1, seen == 0, incremental || s1 == seen + chunk, s1 == Nr};
     }
     seen += chunk;
   }
@@ -933,19 +950,22 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     SV_CHECK_LAUNCH();
     if (!sched[i].last_of_round) continue;
     const bool final_pass = sched[i].final_pass != 0;
-    if (tc && !safe && final_pass) {   // last approximate selection before the exact re-score
+    if (tc && (safe || incremental || final_pass)) {
+      // approximate selection (prunes to ~k + margin), exact re-score of what is not exact yet, exact selection
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
-    }
-    if (tc && (safe || final_pass)) {
       const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
       knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D);
       prof_end(rslot, st);
       SV_CHECK_LAUNCH();
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, final_pass ? kRefineFinal : kRefineExactK, row_offset, q_row0,
+                                              d2_out, idx_out);
+      SV_CHECK_LAUNCH();
+    } else {
+      const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : kRefineSelect);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, row_offset, q_row0, d2_out, idx_out);
+      SV_CHECK_LAUNCH();
     }
-    const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : kRefineSelect);
-    knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, row_offset, q_row0, d2_out, idx_out);
-    SV_CHECK_LAUNCH();
   }
   if (feed)
     for (int i = 0; i < ns; ++i) cudaEventDestroy(ev[i]);
