@@ -467,8 +467,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tc_ld32(taddr + c, v);
           if (row_ok) {
             // 16-byte stores: a warp-wide 4-byte store at a 16 KB row stride touches 32 sectors for 128 useful bytes
+            // (scores only: candidate i of round 0 IS reference row i, the refine kernel knows)
             float* cd = sel.cand_d2 + (size_t)row * kCandCap + (colbase + c - c0);
-            int* ci = sel.cand_idx + (size_t)row * kCandCap + (colbase + c - c0);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const int col = colbase + c + j;
@@ -480,11 +480,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
               }
               if (col + 3 < c1) {
                 *reinterpret_cast<float4*>(cd + j) = make_float4(dd[0], dd[1], dd[2], dd[3]);
-                *reinterpret_cast<int4*>(ci + j) = make_int4(col, col + 1, col + 2, col + 3);
               } else {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (col + u < c1) { cd[j + u] = dd[u]; ci[j + u] = col + u; }
+                  if (col + u < c1) cd[j + u] = dd[u];
               }
             }
           }
@@ -495,19 +494,25 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       } else {
         float* cd = sel.cand_d2 + (size_t)row * kCandCap;
         int* ci = sel.cand_idx + (size_t)row * kCandCap;
-        auto test_chunk = [&](const uint32_t (&v)[32], int col0) -> uint32_t {
+        // test: u = (acc * 2 inv_q) * inv_r - ||r||^2 >= thr; u replaces the accumulator value in v[] because the
+        // survivor's approximate d2 is simply ||q||^2 - u (no second look-up of the column constants)
+        auto test_chunk = [&](uint32_t (&v)[32], int col0) -> uint32_t {
           uint32_t m = 0;
           if (col0 + 32 <= c1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float4 rm = __ldg(rmeta + col0 + j);
-              if (fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x) >= thr) m |= 1u << j;
+              const float u = fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x);
+              v[j] = __float_as_uint(u);
+              if (u >= thr) m |= 1u << j;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float4 rm = __ldg(rmeta + min(col0 + j, c1 - 1));
-              if (col0 + j < c1 && fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x) >= thr) m |= 1u << j;
+              const float u = fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x);
+              v[j] = __float_as_uint(u);
+              if (col0 + j < c1 && u >= thr) m |= 1u << j;
             }
           }
           return m;
@@ -521,8 +526,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             if ((any >> j) & 1u) {            // warp-uniform skip of columns without survivors
               if ((m >> j) & 1u) {
                 if (pos < kCandCap) {
-                  const float4 rm = __ldg(rmeta + col0 + j);
-                  cd[pos] = make_d2_scaled(qnr, rm.x, __uint_as_float(v[j]), cq, rm.y);
+                  cd[pos] = fmaxf(qnr - __uint_as_float(v[j]), 0.f);
                   ci[pos] = col0 + j;
                 }
                 ++pos;
@@ -571,101 +575,9 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 //   kRefineExactK : exact values, conservative schedule.  Same sort, the first k go back to the candidate list
 //                   (count = k exactly, ties broken by index like the final order), tau = T.
 enum { kRefineSelect = 0, kRefineFinal = 1, kRefineExactK = 2 };
-__global__ void __launch_bounds__(256)
-knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, long long row_offset, int q_row0,
-                  float* __restrict__ d2_out, long long* __restrict__ idx_out) {
-  __shared__ __align__(16) unsigned s_v[kCandCap];   // d2 bit patterns   } re-used as 64-bit sort keys
-  __shared__ __align__(16) int s_i[kCandCap];        // candidate rows    } in the final pass
-  __shared__ int s_hist[2048];
-  __shared__ int s_warp[8];
-  __shared__ int s_bin, s_kk, s_out;
-  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  int n = sel.cnt[row];
-  if (n > kCandCap) n = kCandCap;
-  if (mode != kRefineFinal && n <= k) return;
-  float* cd = sel.cand_d2 + (size_t)row * kCandCap;
-  int* ci = sel.cand_idx + (size_t)row * kCandCap;
-  for (int i = tid; i < n; i += 256) { s_v[i] = __float_as_uint(cd[i]); s_i[i] = ci[i]; }
-  int c = n;   // survivors after selection
-  if (n > k) {
-    unsigned prefix = 0, mask = 0;
-    int kk = k;
-#pragma unroll 1
-    for (int pass = 0; pass < 3; ++pass) {
-      const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-      const int bits = pass == 2 ? 10 : 11;
-      for (int b = tid; b < 2048; b += 256) s_hist[b] = 0;
-      __syncthreads();
-      for (int i = tid; i < n; i += 256) {
-        const unsigned v = s_v[i];
-        if ((v & mask) == prefix) atomicAdd(&s_hist[(v >> shift) & ((1u << bits) - 1u)], 1);
-      }
-      __syncthreads();
-      // block scan over 2048 bins (8 per thread) to find the bin holding the kk-th element
-      int loc[8], sum = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) { loc[b] = s_hist[tid * 8 + b]; sum += loc[b]; }
-      int incl = sum;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      if (lane == 31) s_warp[w] = incl;
-      __syncthreads();
-      int base = 0;
-      for (int ww = 0; ww < w; ++ww) base += s_warp[ww];
-      const int excl = base + incl - sum;
-      if (kk > excl && kk <= excl + sum) {
-        int run = excl;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (kk > run && kk <= run + loc[b]) { s_bin = tid * 8 + b; s_kk = kk - run; }
-          run += loc[b];
-        }
-      }
-      __syncthreads();
-      prefix |= (unsigned)s_bin << shift;
-      mask |= ((1u << bits) - 1u) << shift;
-      kk = s_kk;
-      __syncthreads();
-    }
-    const unsigned T = prefix;
-    // approximate scores: everything within 2E of the k-th best may still belong to the exact top k
-    const unsigned keepT = mode == kRefineSelect
-                               ? __float_as_uint(__fadd_ru(__uint_as_float(T), 2.f * row_err_bound(em, q_row0 + row)))
-                               : T;
-    if (tid == 0) s_out = 0;
-    __syncthreads();
-    for (int i = tid; i < n; i += 256) {
-      const unsigned v = s_v[i];
-      if (v <= keepT) {
-        const int pos = atomicAdd(&s_out, 1);
-        cd[pos] = __uint_as_float(v);
-        ci[pos] = s_i[i];
-      }
-    }
-    __syncthreads();
-    c = s_out;
-    if (tid == 0) { sel.cnt[row] = c; sel.tau[row] = __uint_as_float(T); }
-  }
-  if (mode == kRefineSelect) return;
-  // sort the c (~k) survivors by (d2, idx)
-  __syncthreads();
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_v);   // s_v and s_i are contiguous: 32 KB
-  static_assert(sizeof(unsigned) * kCandCap * 2 == sizeof(unsigned long long) * kCandCap, "key aliasing");
-  int P = 1;
-  while (P < c) P <<= 1;
-  unsigned long long mykeys[kCandCap / 256];
-#pragma unroll
-  for (int t = 0; t < kCandCap / 256; ++t) {
-    const int i = tid + t * 256;
-    mykeys[t] = (i < c) ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | (unsigned)(ci[i] & ~kExactFlag)) : ~0ull;
-  }
-  __syncthreads();   // everyone has read cd/ci (global) before the smem region is re-purposed
-#pragma unroll
-  for (int t = 0; t < kCandCap / 256; ++t) {
-    const int i = tid + t * 256;
-    if (i < P) keys[i] = mykeys[t];
-  }
-  __syncthreads();
+constexpr int kSmallSort = 512;   // up to this many candidates: sort them all, no selection passes
+
+__device__ __forceinline__ void bitonic_sort_keys(unsigned long long* keys, int P, int tid) {
   for (int kk2 = 2; kk2 <= P; kk2 <<= 1) {
     for (int j = kk2 >> 1; j > 0; j >>= 1) {
       for (int i = tid; i < P; i += 256) {
@@ -677,6 +589,153 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, long long row_offs
       }
       __syncthreads();
     }
+  }
+}
+
+// dense_first: the candidates are round 0's dense scores (candidate i = reference row i; the filter kernel does not
+// store indices in that round).
+__global__ void __launch_bounds__(256)
+knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, long long row_offset, int q_row0,
+                  float* __restrict__ d2_out, long long* __restrict__ idx_out) {
+  __shared__ __align__(16) unsigned s_v[kCandCap];   // d2 bit patterns   } re-used as 64-bit sort keys
+  __shared__ __align__(16) int s_i[kCandCap];        // candidate rows    }
+  __shared__ int s_hist[256];
+  __shared__ int s_warp[8];
+  __shared__ unsigned s_or[8], s_and[8];
+  __shared__ int s_bin, s_kk, s_out;
+  static_assert(sizeof(unsigned) * kCandCap * 2 == sizeof(unsigned long long) * kCandCap, "key aliasing");
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_v);   // s_v and s_i are contiguous: 32 KB
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  int n = sel.cnt[row];
+  if (n > kCandCap) n = kCandCap;
+  float* cd = sel.cand_d2 + (size_t)row * kCandCap;
+  int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  if (mode != kRefineFinal && n <= k) {
+    if (dense_first)
+      for (int i = tid; i < n; i += 256) ci[i] = i;
+    return;
+  }
+  // Select keeps the exact-flag of a candidate; the exact modes order ties by the bare index
+  const unsigned idmask = mode == kRefineSelect ? 0xffffffffu : (unsigned)~kExactFlag;
+  const float twoE = mode == kRefineSelect ? 2.f * row_err_bound(em, q_row0 + row) : 0.f;
+  int c = n;                       // candidates that reach the sort
+  unsigned T = 0x7f800000u;        // k-th smallest d2 (bit pattern)
+  int P = 1;
+
+  if (n <= kSmallSort) {
+    while (P < n) P <<= 1;
+    for (int i = tid; i < P; i += 256)
+      keys[i] = i < n ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | ((unsigned)(dense_first ? i : ci[i]) & idmask))
+                      : ~0ull;
+    __syncthreads();
+    bitonic_sort_keys(keys, P, tid);
+    if (n > k) T = (unsigned)(keys[k - 1] >> 32);
+    if (mode == kRefineSelect) {   // n > k here; the survivors are a prefix of the sorted list
+      const unsigned keepT = __float_as_uint(__fadd_ru(__uint_as_float(T), twoE));
+      int kept = 0;
+      for (int i0 = 0; i0 < P; i0 += 256) {
+        const int i = i0 + tid;
+        const bool ok = i < n && (unsigned)(keys[i] >> 32) <= keepT;
+        if (ok) { cd[i] = __uint_as_float((unsigned)(keys[i] >> 32)); ci[i] = (int)(unsigned)keys[i]; }
+        kept += __syncthreads_count(ok);
+      }
+      if (tid == 0) { sel.cnt[row] = kept; sel.tau[row] = __uint_as_float(T); }
+      return;
+    }
+    if (n > k && tid == 0) sel.tau[row] = __uint_as_float(T);
+  } else {
+    // ---- radix select of the k-th smallest over the bits in which the candidates differ ----
+    unsigned vor = 0u, vand = 0xffffffffu;
+    for (int i = tid; i < n; i += 256) {
+      const unsigned v = __float_as_uint(cd[i]);
+      s_v[i] = v;
+      s_i[i] = dense_first ? i : ci[i];
+      vor |= v; vand &= v;
+    }
+    vor = __reduce_or_sync(0xffffffffu, vor);
+    vand = __reduce_and_sync(0xffffffffu, vand);
+    if (lane == 0) { s_or[w] = vor; s_and[w] = vand; }
+    __syncthreads();
+    vor = 0u; vand = 0xffffffffu;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) { vor |= s_or[ww]; vand &= s_and[ww]; }
+    // d2 values of one query share their sign / exponent / leading mantissa bits: a digit taken there would send
+    // every candidate to the same histogram bin (serialised shared-memory atomics); start below the common prefix
+    const bool compact = n > k;                            // (n <= k: final pass of a small bank, sort everything)
+    int hi = compact ? 32 - __clz(vor ^ vand) : 0;         // number of low bits that vary (0: all equal)
+    unsigned mask = hi >= 32 ? 0u : ~((1u << hi) - 1u);
+    unsigned prefix = vand & mask;
+    int kk = k;
+    while (hi > 0) {
+      const int lo = hi > 8 ? hi - 8 : 0;
+      const unsigned dm = (1u << (hi - lo)) - 1u;
+      s_hist[tid] = 0;
+      __syncthreads();
+      for (int i = tid; i < n; i += 256) {
+        const unsigned v = s_v[i];
+        if ((v & mask) == prefix) atomicAdd(&s_hist[(v >> lo) & dm], 1);
+      }
+      __syncthreads();
+      const int val = s_hist[tid];
+      int incl = val;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      if (lane == 31) s_warp[w] = incl;
+      __syncthreads();
+      int base = 0;
+      for (int ww = 0; ww < w; ++ww) base += s_warp[ww];
+      const int excl = base + incl - val;
+      if (kk > excl && kk <= excl + val) { s_bin = tid; s_kk = kk - excl; }
+      __syncthreads();
+      prefix |= (unsigned)s_bin << lo;
+      mask |= dm << lo;
+      kk = s_kk;
+      hi = lo;
+    }
+    if (compact) T = prefix;
+    // approximate scores: everything within 2E of the k-th best may still belong to the exact top k
+    const unsigned keepT = mode == kRefineSelect ? __float_as_uint(__fadd_ru(__uint_as_float(T), twoE)) : T;
+    if (tid == 0) s_out = 0;
+    __syncthreads();
+    for (int i0 = 0; compact && i0 < n; i0 += 256) {
+      const int i = i0 + tid;
+      const unsigned v = i < n ? s_v[i] : 0xffffffffu;
+      const bool ok = i < n && v <= keepT;
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      int wbase = 0;
+      if (lane == 0 && bal) wbase = atomicAdd(&s_out, __popc(bal));
+      wbase = __shfl_sync(0xffffffffu, wbase, 0);
+      if (ok) {
+        const int pos = wbase + __popc(bal & ((1u << lane) - 1u));
+        cd[pos] = __uint_as_float(v);
+        ci[pos] = s_i[i];
+      }
+    }
+    __syncthreads();
+    if (compact) {
+      c = s_out;
+      if (tid == 0) { sel.cnt[row] = c; sel.tau[row] = __uint_as_float(T); }
+    }
+    if (mode == kRefineSelect) return;
+    // sort the c (~k) survivors by (d2, idx)
+    while (P < c) P <<= 1;
+    unsigned long long mykeys[kCandCap / 256];
+#pragma unroll
+    for (int t = 0; t < kCandCap / 256; ++t) {
+      const int i = tid + t * 256;
+      mykeys[t] = ~0ull;
+      if (i < c)
+        mykeys[t] = compact ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | ((unsigned)ci[i] & idmask))
+                            : (((unsigned long long)s_v[i] << 32) | ((unsigned)s_i[i] & idmask));
+    }
+    __syncthreads();   // everyone has read its candidates before the smem region is re-purposed
+#pragma unroll
+    for (int t = 0; t < kCandCap / 256; ++t) {
+      const int i = tid + t * 256;
+      if (i < P) keys[i] = mykeys[t];
+    }
+    __syncthreads();
+    bitonic_sort_keys(keys, P, tid);
   }
   if (mode == kRefineExactK) {
     const int keep = c < k ? c : k;
@@ -700,9 +759,13 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, long long row_offs
 }
 
 // Exact re-scoring of the surviving candidates: the single fp16 pass only has to be good enough to discard (its error
-// is bounded, see the header); the <= k + few survivors of each row are re-evaluated with plain fp32 FMAs on the
-// resident fp32 rows (one warp per candidate, lanes stride the channels in float4, shuffle-tree reduction), and the
-// final selection + sort uses these values.
+// is bounded, see the header); the <= k + few survivors of each row that are not exact yet are re-evaluated with plain
+// fp32 FMAs on the resident fp32 rows (one warp per candidate, lanes stride the channels in float4, shuffle-tree
+// reduction), and the final selection + sort uses these values.
+// The gather of ~k rows of 4 D bytes per query (13.6 GB for config 2) is what this kernel costs; it runs at ~7.6 TB/s
+// effective (HBM + ~25 % L2 hits).  r1 experiments that did NOT help: sweeping the bank in L2-sized waves with
+// persistent CTAs (2.1-2.8 ms vs 1.8 ms: the gather is bound by memory-level parallelism, which one CTA per query
+// row with every warp on its own candidate maximises), two candidates per warp iteration (register pressure).
 __global__ void __launch_bounds__(256)
 knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __restrict__ r32,
                    const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int D) {
@@ -893,11 +956,14 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
   int ns = 0;
   for (int seen = 0; seen < Nr;) {
     const int chunk = next_chunk(seen, k, Nr, safe);
-    const int sub = (feed && seen > 0) ? feed->sub_rows : chunk;
-    for (int s0 = seen; s0 < seen + chunk; s0 += sub) {
+    for (int s0 = seen; s0 < seen + chunk;) {
       SV_REQUIRE(ns < 512, "knn: schedule too long");
+      // host-streamed: the last rows arrive in small pieces so that little work is left when the copy ends
+      int sub = chunk;
+      if (feed && seen > 0) sub = (Nr - s0 <= feed->sub_rows) ? (feed->sub_rows / 2 > kTileN ? feed->sub_rows / 2 : kTileN) : feed->sub_rows;
       const int s1 = (s0 + sub < seen + chunk) ? s0 + sub : seen + chunk;
       sched[ns++] = {s0, s1, seen == 0, incremental || s1 == seen + chunk, s1 == Nr};
+      s0 = s1;
     }
     seen += chunk;
   }
@@ -950,20 +1016,21 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     SV_CHECK_LAUNCH();
     if (!sched[i].last_of_round) continue;
     const bool final_pass = sched[i].final_pass != 0;
+    const int dense = (tc && first_round) ? 1 : 0;   // round 0 of the tensor-core filter stores scores only
     if (tc && (safe || incremental || final_pass)) {
       // approximate selection (prunes to ~k + margin), exact re-score of what is not exact yet, exact selection
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, row_offset, q_row0, d2_out, idx_out);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, dense, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
       const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
       knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D);
       prof_end(rslot, st);
       SV_CHECK_LAUNCH();
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, final_pass ? kRefineFinal : kRefineExactK, row_offset, q_row0,
-                                              d2_out, idx_out);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, final_pass ? kRefineFinal : kRefineExactK, 0, row_offset,
+                                              q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
     } else {
       const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : kRefineSelect);
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, row_offset, q_row0, d2_out, idx_out);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, dense, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
     }
   }
@@ -991,7 +1058,7 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
       const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
       sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel[0], rows, 0);
       SV_CHECK_LAUNCH();
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel[0], ErrModel{nullptr, nullptr, 0.f}, k, kRefineFinal, row_offset, q0,
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel[0], ErrModel{nullptr, nullptr, 0.f}, k, kRefineFinal, 0, row_offset, q0,
                                               d2_out, idx_out);
       SV_CHECK_LAUNCH();
     }
@@ -1156,7 +1223,7 @@ extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r
   SV_CHECK_CUDA(cudaMemsetAsync(const_cast<unsigned*>(ta.r.stats), 0, 64 * sizeof(unsigned), st));
   bank_prepare_rows_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(0, Nq, D, bank_out(ta.q));
   SV_CHECK_LAUNCH();
-  HostFeed feed{r_host, cp, 16384};
+  HostFeed feed{r_host, cp, 8192};
   rc = knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out), workspace,
                   workspace_bytes, st, &feed);
   cudaEventDestroy(e0);
