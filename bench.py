@@ -380,7 +380,7 @@ def main():
                      "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": _traffic().get("knn_tc_filter_dram_bytes_per_step"),
                      "traffic_note": "dram read+write bytes of the kernel's launches in one step (ncu --set full, "
-                                     "profiles/r1_ncu_knn_tc_filter_final.txt); algorithmic bytes (Nq+Nr)*D*4 = 0.68 GB",
+                                     "profiles/r1_ncu_knn_f16_final.txt); algorithmic bytes (Nq+Nr)*D*4 = 0.68 GB",
                      "note": "algorithmic 2*D FLOP/pair in ONE fp16 MMA pass (kind::f16, same tensor rate as bf16); the "
                              "filter keeps approx <= T + 2E (rigorous error bound), survivors are re-scored in fp32; "
                              "peak = sustained cuBLAS bf16",
