@@ -917,7 +917,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     AggTcArgs ta;
     ta.R = R; ta.cl_ptr = L.cl_ptr; ta.cl_tok = L.cl_tok; ta.memS = L.memT; ta.cpred = L.cpred; ta.norms = L.norms;
     ta.seg_offsets_host = seg_offsets_host; ta.B = B; ta.N = N; ta.D = D; ta.K = K; ta.S_total = S_total;
-    ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl;
+    ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl; ta.probe = g_agg_dbg;
     const int rc = agg_tc_run(ta, st);
     if (rc != SEGVLAD_OK) return rc;
     if (out_dtype == SEGVLAD_OUT_F64)

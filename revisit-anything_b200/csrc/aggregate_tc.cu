@@ -20,7 +20,8 @@
 //   * thread = segment row (TMEM lane), so norms and scales never leave the thread: no reductions, no CTA barriers.
 // Accumulation is fp32 in TMEM (truncating adds, measured ~4e-8 relative per MMA): <= 3 * n_k / 16 MMAs per element,
 // i.e. ~1e-6 relative for the largest clusters -- inside the 1e-5 descriptor tolerance; the planes are accumulated
-// small-to-large.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-5 epilogue, 6-7 mask-tile builders.
+// small-to-large.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-5 and 8-11 epilogue (two warps per TMEM
+// lane quarter, 64 channels of a pass each), 6-7 mask-tile builders.
 #include "aggregate_tc.cuh"
 
 #include <stdlib.h>
@@ -29,14 +30,18 @@
 
 namespace segvlad {
 
-constexpr int kTcThreadsAgg = 256;
-constexpr int kTcStages = 3;
+constexpr int kTcThreadsAgg = 384;   // warps: 0 TMA, 1 MMA, 2-5 epilogue (column half 0), 6-7 mask builders, 8-11 epilogue (half 1)
+constexpr int kTcStages = 2;
 constexpr uint32_t kTcTileBytes = kTcSegTile * kTcTokChunk * 2;          // 16 KB: one [128 x 64] bf16 operand tile
 constexpr uint32_t kTcStageBytes = 4 * kTcTileBytes;                     // A + 3 B planes
 constexpr int kTcBufs = 512 / kTcPassN;                                  // TMEM accumulator buffers
 constexpr double kEpsTc = 1e-12;
 
-__host__ __device__ constexpr size_t agg_tc_smem() { return 1024 + (size_t)kTcStages * kTcStageBytes + 256; }
+constexpr uint32_t kTcBoxBytes = 32 * 128;                               // output staging box: 32 rows x 128 bytes
+constexpr uint32_t kTcStageOutBytes = 8 * 2 * kTcBoxBytes;               // 8 epilogue warps x 2 boxes
+__host__ __device__ constexpr size_t agg_tc_smem() {
+  return 1024 + (size_t)kTcStages * kTcStageBytes + kTcStageOutBytes + 256 + 2 * 2 * kTcSegTile * 8;
+}
 
 // ------------------------------------------------------------------------------------------------
 // R [B][N][D] fp32 -> RT [3][B][D][Np] bf16 (lo, mid, hi), columns in label-sorted order, zero padded to Np.
@@ -76,6 +81,9 @@ rt_planes_kernel(const float* __restrict__ R, const int* __restrict__ cl_tok, in
 
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// mbarrier wait that adds the cycles spent to a counter when the development probe is on
+#define TC_TIMED_WAIT(bar, par, acc) do { if (probe) { const long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
 
 struct TcItem {
   int b, g0, s0, ns, k, p0, p1, rows, x0, nch, pj0, pj1;   // x0: p0 rounded down to 8 tokens (TMA needs 16-byte
@@ -174,15 +182,53 @@ template <> struct TcOut<float> {
   }
 };
 
+// Output through the TMA instead of the LSU: the scaled values of 32 rows x 128 bytes go to a SWIZZLE_128B staging box
+// (row = lane, 16-byte chunk c stored at c ^ (row & 7): conflict-free for the row-per-lane pattern) and ONE
+// cp.async.bulk.tensor store moves the box.  r1 ncu: with direct 256-bit stores the L1 data pipe (64 bytes per wavefront
+// for the row-per-lane pattern) was the busiest unit of the kernel, 100 % busy during the write sweep.
+template <typename OutT> struct TcStage;
+template <> struct TcStage<double> {
+  static constexpr int kCols = 16;
+  template <int kOff>
+  static __device__ __forceinline__ void put(uint32_t sb, int lane, const uint32_t (&v)[32], double sc) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(sb + lane * 128 + ((c ^ (lane & 7)) << 4)),
+                   "d"((double)__uint_as_float(v[kOff + 2 * c]) * sc), "d"((double)__uint_as_float(v[kOff + 2 * c + 1]) * sc)
+                   : "memory");
+  }
+};
+template <> struct TcStage<float> {
+  static constexpr int kCols = 32;
+  template <int kOff>
+  static __device__ __forceinline__ void put(uint32_t sb, int lane, const uint32_t (&v)[32], double sc) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + lane * 128 + ((c ^ (lane & 7)) << 4)),
+                   "f"((float)((double)__uint_as_float(v[4 * c]) * sc)), "f"((float)((double)__uint_as_float(v[4 * c + 1]) * sc)),
+                   "f"((float)((double)__uint_as_float(v[4 * c + 2]) * sc)), "f"((float)((double)__uint_as_float(v[4 * c + 3]) * sc))
+                   : "memory");
+  }
+};
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kTcThreadsAgg, 1)
-aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __restrict__ tile_tbl,
+aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_constant__ CUtensorMap map_out,
+                    const int* __restrict__ tile_tbl,
                     const int* __restrict__ cl_ptr, const uint16_t* __restrict__ memS, const int* __restrict__ cpred,
-                    int B, int N, int D, int K, int n_items, int J, OutT* __restrict__ out, double* __restrict__ norms) {
+                    int B, int N, int D, int K, int n_items, int J, OutT* __restrict__ out, double* __restrict__ norms,
+                    unsigned long long* __restrict__ probe, int stagger) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes);
+  uint8_t* stage_out = smem + kTcStages * kTcStageBytes;   // [8 epilogue warps][2 boxes][4 KB], 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kTcStageOutBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  double* s_ssq = reinterpret_cast<double*>(bars + 32);   // [2 item parities][2 column halves][128 rows] partial sums of squares
   const uint32_t bar_full = smem_u32(bars + 0);      // [kTcStages] A written (2 builder warps) + B landed (TMA)
   const uint32_t bar_empty = smem_u32(bars + 4);     // [kTcStages] MMAs that read the stage retired
   const uint32_t bar_tfull = smem_u32(bars + 8);     // [kTcBufs]   accumulator pass complete
@@ -192,7 +238,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTcStages; ++i) { mbar_init(bar_full + 8 * i, 3); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < kTcBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < kTcBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -203,12 +249,17 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (stagger > 0) {   // experiment: de-phase the CTAs (norm sweeps are DRAM-idle, write sweeps DRAM-bound)
+    const long long t0 = clock64(), wait = (long long)(blockIdx.x % 3) * stagger;
+    while (clock64() - t0 < wait) { }
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rt) : "memory");
       uint32_t stage = 0, phase = 0;
+      long long t_wait = 0;
       for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
         const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
         if (it.rows == 0) continue;
@@ -216,7 +267,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
         for (int inst = 0; inst < n_inst; ++inst) {
           const int pass = inst < P ? inst : it.pj0 + inst - P;
           for (int c = 0; c < it.nch; ++c) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            TC_TIMED_WAIT(bar_empty + 8 * stage, phase ^ 1, t_wait);
             const uint32_t sb = smem_u32(smem + stage * kTcStageBytes) + kTcTileBytes;
             const uint32_t fb = bar_full + 8 * stage;
             mbar_arrive_expect_tx(fb, 3 * kTcTileBytes);
@@ -227,11 +278,14 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
           }
         }
       }
+      if (probe) probe[blockIdx.x * 16 + 9] = t_wait;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, ti = 0;
+      long long t_tempty = 0, t_full = 0;
+      const long long t_begin = clock64();
       for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
         const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
         if (it.rows == 0) continue;
@@ -243,11 +297,11 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) |
                                  ((uint32_t)(kTcSegTile >> 4) << 24);
           const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-          mbar_wait(bar_tempty + 8 * buf, (use & 1) ^ 1);
+          TC_TIMED_WAIT(bar_tempty + 8 * buf, (use & 1) ^ 1, t_tempty);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * kTcPassN;
           for (int c = 0; c < it.nch; ++c) {
-            mbar_wait(bar_full + 8 * stage, phase);
+            TC_TIMED_WAIT(bar_full + 8 * stage, phase, t_full);
             tc_fence_after();
             const uint32_t sa = smem_u32(smem + stage * kTcStageBytes);
             const uint64_t adesc = umma_desc_sw128(sa);
@@ -265,11 +319,15 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
           tc_commit(bar_tfull + 8 * buf);
         }
       }
+      if (probe) { probe[blockIdx.x * 16 + 6] = t_tempty; probe[blockIdx.x * 16 + 7] = t_full;
+                   probe[blockIdx.x * 16 + 8] = clock64() - t_begin; }
     }
-  } else if (warp >= 6) {
+  } else if (warp == 6 || warp == 7) {
     // ===================== mask-tile builders (64 threads) =====================
     const int u = threadIdx.x - 192;
     uint32_t stage = 0, phase = 0;
+    long long t_bwait = 0;
+    const long long t_bbegin = clock64();
     for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
       const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
       if (it.rows == 0) continue;
@@ -297,7 +355,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
             }
             cached_c = c;
           }
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          TC_TIMED_WAIT(bar_empty + 8 * stage, phase ^ 1, t_bwait);
           const uint32_t sa = smem_u32(smem + stage * kTcStageBytes);
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
@@ -305,12 +363,11 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               // row = 8 g + j of the SWIZZLE_128B K-major tile: 128-byte row, 16-byte chunk c8 stored at c8 ^ (row & 7)
+              // bit j of both 16-bit membership words -> two bf16 1.0 / 0.0 in one shift, mask and multiply
+              // (r1 ncu: the select-per-bit form made the two builder warps the critical path of the whole kernel)
               uint32_t o[4];
 #pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                const uint32_t wv = wlo[r][h];
-                o[h] = (((wv >> j) & 1u) ? 0x3F80u : 0u) | (((wv >> (16 + j)) & 1u) ? 0x3F800000u : 0u);
-              }
+              for (int h = 0; h < 4; ++h) o[h] = ((wlo[r][h] >> j) & 0x00010001u) * 0x3F80u;
               const uint32_t addr = sa + g * 1024 + j * 128 + ((c8 ^ j) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
             }
@@ -322,86 +379,128 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const int* __res
         }
       }
     }
+    if (probe && threadIdx.x == 192) { probe[blockIdx.x * 16 + 10] = t_bwait; probe[blockIdx.x * 16 + 11] = clock64() - t_bbegin; }
   } else {
     // ===================== epilogue warps: thread = segment row (TMEM lane) =====================
-    const int quarter = warp & 3;
+    // Two warps per TMEM lane quarter, each owning 64 of a pass's 128 channels: one warp per scheduler could not hide
+    // its own tcgen05.ld -> convert -> store latencies (r1 ncu: 12.5 % warps active, issue slots 19 % busy at 62 % of the
+    // HBM write roofline).  The two halves of a row exchange their partial sums of squares through shared memory.
+    const int quarter = warp & 3, half = warp >= 8 ? 1 : 0;
     const int row = quarter * 32 + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t ti = 0;
+    const uint32_t my_stage = smem_u32(stage_out) + (uint32_t)(half * 4 + quarter) * 2 * kTcBoxBytes;
+    const bool tma_dims = (D % 64) == 0;      // every pass piece of this warp is 0 or 32 columns wide
+    uint32_t ti = 0, n_done = 0, nbox = 0;
+    long long t_nwait = 0, t_bar = 0, t_wwait = 0, t_store = 0;
+    const long long t_ebegin = clock64();
     for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
       const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
       const bool valid = row < it.ns;
+      const bool tma_rows = tma_dims && (quarter * 32 + 32 <= it.ns);
       const int s = it.s0 + row;
       OutT* orow = out + ((size_t)(valid ? s : it.s0) * K + it.k) * D;
       if (it.rows == 0) {
         // empty cluster: the block is zero for every segment
         if (valid) {
-          if (it.pj0 == 0) norms[(size_t)s * K + it.k] = 0.0;
+          if (it.pj0 == 0 && half == 0) norms[(size_t)s * K + it.k] = 0.0;
           const int d_beg = it.pj0 * kTcPassN, d_end = min(D, it.pj1 * kTcPassN);
-          for (int d = d_beg; d < d_end; d += 16) TcOut<OutT>::zero16(orow + d);
+          for (int d = d_beg + 16 * half; d < d_end; d += 32) TcOut<OutT>::zero16(orow + d);
         }
         continue;
       }
-      // ---- norm sweep: sum of squares of the whole block row (fp32 products, fp64 accumulation per 32 columns) ----
+      // ---- norm sweep: sum of squares of this warp's half of the block row (fp32 products, fp64 accumulation) ----
       double ssq = 0.0;
       for (int pass = 0; pass < P; ++pass, ++ti) {
         const int width = min(kTcPassN, D - pass * kTcPassN);
-        const int np = (width + 31) >> 5;
+        const int c0 = half * 64;
+        const int w0 = min(32, width - c0), w1 = min(32, width - c0 - 32);     // columns in this warp's two pieces
         const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-        mbar_wait(bar_tfull + 8 * buf, use & 1);
+        TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_nwait);
         tc_fence_after();
-        const uint32_t tcol = tlane + buf * kTcPassN;
+        const uint32_t tcol = tlane + buf * kTcPassN + c0;
         uint32_t va[32], vb[32];
-        tc_ld32_issue(tcol, va);
-        tc_ld_wait(va);
-#pragma unroll 1
-        for (int cc = 0; cc < np; cc += 2) {
-          if (cc + 1 < np) tc_ld32_issue(tcol + (cc + 1) * 32, vb);      // next piece loads while this one is reduced
-          ssq += (double)tc_sumsq(va, min(32, width - cc * 32));
-          if (cc + 1 < np) {
-            tc_ld_wait(vb);
-            if (cc + 2 < np) tc_ld32_issue(tcol + (cc + 2) * 32, va);
-            ssq += (double)tc_sumsq(vb, min(32, width - (cc + 1) * 32));
-            if (cc + 2 < np) tc_ld_wait(va);
-          }
+        if (w0 > 0) {                                  // (warp-uniform)
+          tc_ld32_issue(tcol, va);
+          if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
+          tc_ld_wait(va);
+          ssq += (double)tc_sumsq(va, w0);
+          if (w1 > 0) { tc_ld_wait(vb); ssq += (double)tc_sumsq(vb, w1); }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       }
+      double* xs = s_ssq + (n_done & 1) * 2 * kTcSegTile;
+      xs[half * kTcSegTile + row] = ssq;
+      { const long long _t = probe ? clock64() : 0;
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+        if (probe) t_bar += clock64() - _t; }
+      ssq = xs[row] + xs[kTcSegTile + row];
+      ++n_done;
       const double nrm = sqrt(ssq);
       double sc = 0.0;
       if (valid) {
-        if (it.pj0 == 0) norms[(size_t)s * K + it.k] = nrm;
+        if (it.pj0 == 0 && half == 0) norms[(size_t)s * K + it.k] = nrm;
         sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cpred[s]), kEpsTc));
       }
       // ---- write sweep: accumulator x scale -> fp64 -> 32-byte vector stores (each lane fills whole sectors of its row) ----
       for (int pass = it.pj0; pass < it.pj1; ++pass, ++ti) {
         const int width = min(kTcPassN, D - pass * kTcPassN);
-        const int np = (width + 31) >> 5;
+        const int c0 = half * 64;
+        const int w0 = min(32, width - c0), w1 = min(32, width - c0 - 32);
         const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-        mbar_wait(bar_tfull + 8 * buf, use & 1);
+        TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_wwait);
         tc_fence_after();
-        const uint32_t tcol = tlane + buf * kTcPassN;
-        OutT* op = orow + (size_t)pass * kTcPassN;
+        const long long t_s0 = probe ? clock64() : 0;
+        const uint32_t tcol = tlane + buf * kTcPassN + c0;
+        OutT* op = orow + (size_t)pass * kTcPassN + c0;
         uint32_t va[32], vb[32];
-        tc_ld32_issue(tcol, va);
-        tc_ld_wait(va);
-#pragma unroll 1
-        for (int cc = 0; cc < np; cc += 2) {
-          if (cc + 1 < np) tc_ld32_issue(tcol + (cc + 1) * 32, vb);
-          if (valid) TcOut<OutT>::store(op + cc * 32, va, sc, min(32, width - cc * 32));
-          if (cc + 1 < np) {
-            tc_ld_wait(vb);
-            if (cc + 2 < np) tc_ld32_issue(tcol + (cc + 2) * 32, va);
-            if (valid) TcOut<OutT>::store(op + (cc + 1) * 32, vb, sc, min(32, width - (cc + 1) * 32));
-            if (cc + 2 < np) tc_ld_wait(va);
-          }
+        if (w0 > 0) {
+          tc_ld32_issue(tcol, va);
+          if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
+          tc_ld_wait(va);
+          if (w1 > 0) tc_ld_wait(vb);
         }
+        // the accumulator is in registers: hand the TMEM buffer back before the (slow) stores
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (tma_rows && w0 == 32) {                      // (warp-uniform) all 32 rows valid, full 32-column pieces
+          const int xcol = it.k * D + pass * kTcPassN + c0;
+          const int yrow = it.s0 + quarter * 32;
+          auto flush = [&](int x) {                      // box staged by all lanes -> one bulk tensor store
+            tc_fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&map_out, my_stage + (nbox & 1) * kTcBoxBytes, x, yrow);
+            ++nbox;
+          };
+          auto acquire = [&]() -> uint32_t {             // the box used two stores ago has been read by the TMA
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            return my_stage + (nbox & 1) * kTcBoxBytes;
+          };
+          if constexpr (sizeof(OutT) == 8) {
+            uint32_t sb = acquire(); TcStage<OutT>::template put<0>(sb, lane, va, sc); flush(xcol);
+            sb = acquire(); TcStage<OutT>::template put<16>(sb, lane, va, sc); flush(xcol + 16);
+            if (w1 == 32) {
+              sb = acquire(); TcStage<OutT>::template put<0>(sb, lane, vb, sc); flush(xcol + 32);
+              sb = acquire(); TcStage<OutT>::template put<16>(sb, lane, vb, sc); flush(xcol + 48);
+            }
+          } else {
+            uint32_t sb = acquire(); TcStage<OutT>::template put<0>(sb, lane, va, sc); flush(xcol);
+            if (w1 == 32) { sb = acquire(); TcStage<OutT>::template put<0>(sb, lane, vb, sc); flush(xcol + 32); }
+          }
+        } else if (valid && w0 > 0) {
+          TcOut<OutT>::store(op, va, sc, w0);
+          if (w1 > 0) TcOut<OutT>::store(op + 32, vb, sc, w1);
+        }
+        if (probe) t_store += clock64() - t_s0;
       }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging boxes drained before exit
+    if (probe && warp == 2 && lane == 0) {
+      unsigned long long* pr = probe + blockIdx.x * 16;
+      pr[0] = clock64() - t_ebegin; pr[1] = t_nwait; pr[3] = t_bar; pr[4] = t_wwait; pr[5] = t_store; pr[12] = n_done;
     }
   }
   tc_fence_before();
@@ -422,10 +521,25 @@ bool agg_tc_supported(int N, int D, int K) {
 template <typename OutT>
 static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, int J, int grid, cudaStream_t st) {
   const size_t smem = agg_tc_smem();
+  const char* se = getenv("SEGVLAD_AGG_STAGGER");
+  const int stagger = se ? atoi(se) : 0;
+  // output [S_total][K*D] as a 2-D tensor: the epilogue stores 32-row x 128-byte boxes through the TMA
+  CUtensorMap map_out;
+  {
+    PFN_encodeTiled enc = get_encode();
+    cuuint64_t dims[2] = {(cuuint64_t)a.K * a.D, (cuuint64_t)a.S_total};
+    cuuint64_t strides[1] = {(cuuint64_t)a.K * a.D * sizeof(OutT)};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(OutT)), 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&map_out, sizeof(OutT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
+  }
   SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
-  aggregate_tc_kernel<OutT><<<grid, kTcThreadsAgg, smem, st>>>(map, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K,
-                                                             n_items, J, reinterpret_cast<OutT*>(a.out), a.norms);
+  aggregate_tc_kernel<OutT><<<grid, kTcThreadsAgg, smem, st>>>(map, map_out, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K,
+                                                             n_items, J, reinterpret_cast<OutT*>(a.out), a.norms, a.probe, stagger);
   prof_end(pslot, st);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;

@@ -24,6 +24,7 @@ struct AggTcArgs {
   int out_dtype;
   __nv_bfloat16* RT;          // workspace: [3 planes][B][D][Np] transposed, label-sorted bf16 split of R
   int* tile_tbl;              // workspace: [n_tiles][4] = image, first group, first segment, #segments
+  unsigned long long* probe;  // development aid: per-CTA cycle counters [grid][16] (segvlad_debug_aggregate_probe), or null
 };
 
 inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcTokChunk); }
