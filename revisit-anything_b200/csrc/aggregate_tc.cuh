@@ -8,7 +8,8 @@
 namespace segvlad {
 
 constexpr int kTcSegTile = 128;   // segments per MMA tile (M)
-constexpr int kTcTokChunk = 64;   // tokens per K chunk (one 128-byte swizzle row of bf16)
+constexpr int kTcTokChunk = 32;   // tokens per K chunk (one 64-byte swizzle row of bf16)
+constexpr int kTcNpAlign = 64;    // the label-sorted token axis of RT is padded to this many tokens
 constexpr int kTcPassN = 128;     // descriptor channels per accumulator pass (N)
 
 struct AggTcArgs {
@@ -27,7 +28,7 @@ struct AggTcArgs {
   unsigned long long* probe;  // development aid: per-CTA cycle counters [grid][16] (segvlad_debug_aggregate_probe), or null
 };
 
-inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcTokChunk); }
+inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcNpAlign); }
 inline size_t agg_tc_rt_elems(int B, int N, int D) { return (size_t)3 * B * D * agg_tc_np(N); }
 inline int agg_tc_max_tiles(int B, int S_total) { return S_total / kTcSegTile + B; }
 bool agg_tc_supported(int N, int D, int K);

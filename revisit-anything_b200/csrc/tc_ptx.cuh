@@ -76,8 +76,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
          (2ull << 61);
 }
-
-
+// Same for SWIZZLE_64B (layout_type 4): 64-byte rows, SBO = 512 B (8 rows x 64 B)
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) |
+         (4ull << 61);
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query: the library carries no link-time dependency on
 // libcuda and loads on machines without a GPU.
