@@ -875,6 +875,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
 
   const float* R = L.R;
   const int* labels = L.labels;
+  bool fused_rt = false;
   if (residuals_in) {
     R = residuals_in;
     labels = labels_in;
@@ -889,8 +890,11 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
       SV_CHECK_LAUNCH();
       assign_finalize_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(L.part, L.ssq, N, K, Kp, prenorm, L.labels, L.nrm);
       SV_CHECK_LAUNCH();
-      residual_dn_kernel<<<dim3((N + 31) / 32, B, (D + 255) / 256), 256, 0, st>>>(tokens, N, D, centers, L.labels, L.nrm,
-                                                                               L.R);
+      // tensor-core path: the residual planes are built straight from the tokens after the cluster lists (no R)
+      fused_rt = use_tc && agg_tc_fused_channels(N, K) > 0;
+      if (!fused_rt)
+        residual_dn_kernel<<<dim3((N + 31) / 32, B, (D + 255) / 256), 256, 0, st>>>(tokens, N, D, centers, L.labels, L.nrm,
+                                                                                 L.R);
     } else {
       dim3 grid((N + 7) / 8, B);
       assign_nd_kernel<<<grid, 256, 0, st>>>(tokens, N, D, centers, L.chatT, K, Kp, prenorm, L.R, L.labels);
@@ -915,7 +919,8 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
   if (use_tc) {
     // tensor-core path: mask tile x bf16-split residual planes per (image, 128-segment tile, cluster)
     AggTcArgs ta;
-    ta.R = R; ta.cl_ptr = L.cl_ptr; ta.cl_tok = L.cl_tok; ta.memS = L.memT; ta.cpred = L.cpred; ta.norms = L.norms;
+    ta.R = fused_rt ? nullptr : R; ta.tokens_dn = tokens; ta.centers = centers; ta.labels = L.labels; ta.nrm = L.nrm;
+    ta.cl_ptr = L.cl_ptr; ta.cl_tok = L.cl_tok; ta.memS = L.memT; ta.cpred = L.cpred; ta.norms = L.norms;
     ta.seg_offsets_host = seg_offsets_host; ta.B = B; ta.N = N; ta.D = D; ta.K = K; ta.S_total = S_total;
     ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl; ta.probe = g_agg_dbg;
     const int rc = agg_tc_run(ta, st);

@@ -8,12 +8,15 @@
 namespace segvlad {
 
 constexpr int kTcSegTile = 128;   // segments per MMA tile (M)
-constexpr int kTcTokChunk = 32;   // tokens per K chunk (one 64-byte swizzle row of bf16)
-constexpr int kTcNpAlign = 64;    // the label-sorted token axis of RT is padded to this many tokens
+constexpr int kTcTokChunk = 64;   // tokens per K chunk (one 128-byte swizzle row of bf16)
 constexpr int kTcPassN = 128;     // descriptor channels per accumulator pass (N)
 
 struct AggTcArgs {
-  const float* R;             // [B][N][D] fp32 residual rows (token-major)
+  const float* R;             // [B][N][D] fp32 residual rows (token-major), or null: build RT from the tokens (below)
+  const float* tokens_dn;     // [B][D][N] tokens, centres [K][D], labels [B][N], ||x|| [B][N] (used when R is null)
+  const float* centers;
+  const int* labels;
+  const float* nrm;
   const int* cl_ptr;          // [B][K+1] cluster boundaries in the label-sorted token order
   const int* cl_tok;          // [B][N]   label-sorted token ids
   const uint16_t* memS;       // [n_groups][N] membership words (bit j = segment 8*g + j), label-sorted order
@@ -28,10 +31,11 @@ struct AggTcArgs {
   unsigned long long* probe;  // development aid: per-CTA cycle counters [grid][16] (segvlad_debug_aggregate_probe), or null
 };
 
-inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcNpAlign); }
+inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcTokChunk); }
 inline size_t agg_tc_rt_elems(int B, int N, int D) { return (size_t)3 * B * D * agg_tc_np(N); }
 inline int agg_tc_max_tiles(int B, int S_total) { return S_total / kTcSegTile + B; }
 bool agg_tc_supported(int N, int D, int K);
+int agg_tc_fused_channels(int N, int K);               // > 0: RT can be built straight from [D][N] tokens
 int agg_tc_run(const AggTcArgs& a, cudaStream_t st);   // returns SEGVLAD_* status
 
 }  // namespace segvlad

@@ -23,9 +23,8 @@ lib.segvlad_debug_aggregate_probe(None)
 a = buf.cpu().numpy().reshape(-1, 16)
 a = a[a[:, 0] > 0]
 print("CTAs", len(a))
-names = {0: "write warps total", 14: "write: wait block norm (mailbox)", 4: "write: wait tfull", 5: "write: ld+stage+store",
-         3: "norm warps total", 1: "norm: wait tfull", 2: "norm: wait mailbox slot",
-         8: "mma total", 6: "mma: wait tempty (write bufs)", 13: "mma: wait tempty (norm bufs)", 7: "mma: wait full",
+names = {0: "epi total", 1: "epi wait tfull (norm sweep)", 3: "epi bar.sync", 4: "epi wait tfull (write sweep)",
+         5: "epi ld+stage+store (write sweep)", 6: "mma wait tempty", 7: "mma wait full", 8: "mma total",
          9: "producer wait empty", 10: "builder wait empty", 11: "builder total", 12: "items"}
 for i, n in names.items():
     print(f"{n:36s} mean {a[:, i].mean():12.0f}  min {a[:, i].min():10d}  max {a[:, i].max():10d}")
