@@ -782,6 +782,7 @@ struct AggLayout {
   float* chatT; float* R; float* part; float* ssq; float* nrm; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT; int* gcnt;
   int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
   __nv_bfloat16* RT; int* tile_tbl;   // tensor-core path (aggregate_tc.cu)
+  __nv_bfloat16* chat_planes;         // tensor-core assignment (assign_tc.cu)
   size_t total;
 };
 
@@ -810,6 +811,7 @@ static AggLayout carve_agg(void* ws, int B, int N, int D, int K, int S_total) {
   L.grp_nseg = c.take<int>(max_groups);
   L.RT = c.take<__nv_bfloat16>(agg_tc_supported(N, D, K) ? agg_tc_rt_elems(B, N, D) : 0);
   L.tile_tbl = c.take<int>((size_t)4 * agg_tc_max_tiles(B, S_total));
+  L.chat_planes = c.take<__nv_bfloat16>(assign_tc_workspace_elems(D, K));
   L.total = c.total();
   return L;
 }
@@ -880,16 +882,24 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     R = residuals_in;
     labels = labels_in;
   } else {
-    // zero padding columns of chatT (k >= K) so the 32-wide loads see zeros
-    SV_CHECK_CUDA(cudaMemsetAsync(L.chatT, 0, sizeof(float) * (size_t)D * Kp, st));
-    normalize_centers_kernel<<<K, 256, 0, st>>>(centers, K, D, L.chatT, Kp);
-    SV_CHECK_LAUNCH();
+    const bool asg_tc = layout == SEGVLAD_TOKENS_DN && assign_tc_supported(N, D, K);
+    if (!asg_tc) {
+      // zero padding columns of chatT (k >= K) so the 32-wide loads see zeros
+      SV_CHECK_CUDA(cudaMemsetAsync(L.chatT, 0, sizeof(float) * (size_t)D * Kp, st));
+      normalize_centers_kernel<<<K, 256, 0, st>>>(centers, K, D, L.chatT, Kp);
+      SV_CHECK_LAUNCH();
+    }
     if (layout == SEGVLAD_TOKENS_DN) {
-      assign_partial_kernel<<<dim3((N + kAsgTok - 1) / kAsgTok, B, kAsgSplit), 128, 0, st>>>(tokens, N, D, L.chatT, K, Kp,
-                                                                                          L.part, L.ssq);
-      SV_CHECK_LAUNCH();
-      assign_finalize_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(L.part, L.ssq, N, K, Kp, prenorm, L.labels, L.nrm);
-      SV_CHECK_LAUNCH();
+      if (asg_tc) {
+        const int rc = assign_tc_run(tokens, B, N, D, centers, K, prenorm, L.chat_planes, L.labels, L.nrm, st);
+        if (rc != SEGVLAD_OK) return rc;
+      } else {
+        assign_partial_kernel<<<dim3((N + kAsgTok - 1) / kAsgTok, B, kAsgSplit), 128, 0, st>>>(tokens, N, D, L.chatT, K, Kp,
+                                                                                            L.part, L.ssq);
+        SV_CHECK_LAUNCH();
+        assign_finalize_kernel<<<dim3((N + 127) / 128, B), 128, 0, st>>>(L.part, L.ssq, N, K, Kp, prenorm, L.labels, L.nrm);
+        SV_CHECK_LAUNCH();
+      }
       // tensor-core path: the residual planes are built straight from the tokens after the cluster lists (no R)
       fused_rt = use_tc && agg_tc_fused_channels(N, K) > 0;
       if (!fused_rt)

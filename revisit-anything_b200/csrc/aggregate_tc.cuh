@@ -38,4 +38,10 @@ bool agg_tc_supported(int N, int D, int K);
 int agg_tc_fused_channels(int N, int K);               // > 0: RT can be built straight from [D][N] tokens
 int agg_tc_run(const AggTcArgs& a, cudaStream_t st);   // returns SEGVLAD_* status
 
+// Tensor-core cosine assignment for [D][N] tokens (assign_tc.cu): labels [B][N], nrm [B][N] = max(||x||, eps) (1 if prenorm)
+bool assign_tc_supported(int N, int D, int K);
+size_t assign_tc_workspace_elems(int D, int K);        // bf16 elements for the c_hat planes
+int assign_tc_run(const float* tokens, int B, int N, int D, const float* centers, int K, int prenorm,
+                  __nv_bfloat16* chat_planes, int* labels, float* nrm, cudaStream_t st);
+
 }  // namespace segvlad

@@ -173,3 +173,36 @@ def test_bad_arguments_raise():
     with pytest.raises(ValueError):
         engine.aggregate_batch(torch.zeros(30 * 6, device=dev), 30, 6, TOKENS_DN, torch.zeros(32, 6, device=dev),
                                torch.zeros((1, 1), dtype=torch.int32, device=dev), [1])   # D % 4 != 0
+
+
+@pytest.mark.parametrize("B,D,K,H,W", [(3, 1536, 32, 480, 640), (2, 768, 128, 322, 322), (2, 1520, 64, 196, 266),
+                                       (1, 64, 8, 140, 182)])
+def test_tensor_core_assignment_matches_simt_assignment(monkeypatch, B, D, K, H, W):
+    # labels / ||x|| from the tcgen05 kernel (csrc/assign_tc.cu: three bf16 pieces, six products) against the SIMT fp32
+    # kernels (SEGVLAD_ASSIGN_TC=0) and the oracle's fp64 argmax; D = 1520 ends in a partial 64-channel stage, N = 529 is odd
+    dev = torch.device("cuda")
+    dh, dw = H // 14, W // 14
+    N = dh * dw
+    centers = synth.make_centers(K, D, 40 + K)
+    toks = torch.stack([synth.make_tokens(D, dh, dw, 900 + i, centers).reshape(D, N) for i in range(B)])
+    if D == 64:
+        toks = toks * 37.5                                   # un-normalised tokens: ||x|| is computed by the kernel
+    S = 5
+    member = torch.rand(B * S, N, generator=torch.Generator().manual_seed(1)) < 0.5
+    bits = engine.pack_membership(member.to(dev))
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SEGVLAD_ASSIGN_TC", mode)
+        outs[mode] = engine.aggregate_batch(toks.to(dev), N, D, TOKENS_DN, centers.to(dev), bits, [S] * B, None,
+                                            return_labels=True)
+    lab_tc, lab_simt = outs["1"][1].cpu().numpy(), outs["0"][1].cpu().numpy()
+    n_safe = 0
+    for b in range(B):
+        want, margin = O.assign_labels(torch.nn.functional.normalize(toks[b].t().contiguous(), dim=1), centers)
+        safe = margin.numpy() > 1e-5
+        n_safe += int(safe.sum())
+        np.testing.assert_array_equal(lab_tc[b][safe], want.numpy()[safe])
+        np.testing.assert_array_equal(lab_simt[b][safe], want.numpy()[safe])
+    assert n_safe > 0.99 * B * N
+    if (lab_tc == lab_simt).all():
+        _cmp(outs["1"][0].cpu().numpy(), outs["0"][0].cpu().numpy())
