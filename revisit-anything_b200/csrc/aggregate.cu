@@ -286,13 +286,11 @@ cluster_lists_kernel(const int* __restrict__ labels, int N, int K, int* __restri
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int* lab = labels + (size_t)b * N;
   __shared__ int s_cnt[256 + 1];
-  for (int k = w; k < K; k += nw) {
-    int c = 0;
-    for (int base = 0; base < N; base += 32) {
-      int p = base + lane;
-      c += __popc(__ballot_sync(0xffffffffu, p < N && lab[p] == k));
-    }
-    if (lane == 0) s_cnt[k] = c;
+  for (int k = threadIdx.x; k <= K; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {   // histogram (integer: order-free); caller labels outside [0, K) are ignored
+    const int l = lab[p];
+    if ((unsigned)l < (unsigned)K) atomicAdd(&s_cnt[l], 1);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -733,15 +731,19 @@ __global__ void rownorm_fixup_kernel(const double* __restrict__ norms, const int
                                      size_t row_len, OutT* __restrict__ out) {
   const int s = blockIdx.x;
   __shared__ double s_factor;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // q is exactly 0 or 1 for every block except the degenerate ones, so the sum is exact in any order
     double tsum = 0.0;
-    for (int k = 0; k < K; ++k) {
+    for (int k = threadIdx.x; k < K; k += 32) {
       double n = norms[(size_t)s * K + k];
       double q = n / fmax(n, kEpsD);
       tsum += q * q;
     }
-    double m_true = sqrt(tsum), m_pred = sqrt((double)cpred[s]);
-    s_factor = (m_true == m_pred) ? 1.0 : fmax(m_pred, kEpsD) / fmax(m_true, kEpsD);
+    tsum = warp_sum(tsum);
+    if (threadIdx.x == 0) {
+      double m_true = sqrt(tsum), m_pred = sqrt((double)cpred[s]);
+      s_factor = (m_true == m_pred) ? 1.0 : fmax(m_pred, kEpsD) / fmax(m_true, kEpsD);
+    }
   }
   __syncthreads();
   const double f = s_factor;

@@ -166,12 +166,18 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
     const bool valid = p < N;
     const float* tok = tokens + (size_t)b * D * N + p;
     float ssq = 0.f;
+    float x[32], xn[32];   // this stage's channels and the next stage's (loads in flight while this one is converted)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xn[j] = (valid && h * 32 + j < D) ? __ldg(tok + (size_t)(h * 32 + j) * N) : 0.f;
     for (int s = 0; s < n_st; ++s) {
       const int stage = s % kAtStages, use = s / kAtStages;
-      const int d0 = s * kAtCh + h * 32;
-      float x[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) x[j] = (valid && d0 + j < D) ? __ldg(tok + (size_t)(d0 + j) * N) : 0.f;
+      for (int j = 0; j < 32; ++j) x[j] = xn[j];
+      if (s + 1 < n_st) {
+        const int d1 = (s + 1) * kAtCh + h * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xn[j] = (valid && d1 + j < D) ? __ldg(tok + (size_t)(d1 + j) * N) : 0.f;
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) ssq = fmaf(x[j], x[j], ssq);
       mbar_wait(bar_empty + 8 * stage, (use & 1) ^ 1);
