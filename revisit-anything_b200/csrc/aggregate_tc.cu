@@ -130,7 +130,9 @@ rt_from_tokens_kernel(const float* __restrict__ tokens, const float* __restrict_
 
 // channels per CTA of rt_from_tokens_kernel (0: the rows do not fit in shared memory -> two-kernel path)
 int agg_tc_fused_channels(int N, int K) {
-  for (int ch = 8; ch >= 1; ch >>= 1)
+  const char* e = getenv("SEGVLAD_RT_CH");   // development: upper limit of the channels per CTA (measured 2/4/8/16: 125/101/107/135 us)
+  const int top = e ? atoi(e) : 4;
+  for (int ch = top; ch >= 1; ch >>= 1)
     if (((size_t)ch * N + 4 + (size_t)K * ch) * sizeof(float) <= 100 * 1024) return ch;
   return 0;
 }

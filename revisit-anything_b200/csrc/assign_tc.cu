@@ -235,7 +235,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
 bool assign_tc_supported(int N, int D, int K) {
   const char* e = getenv("SEGVLAD_ASSIGN_TC");   // "0" selects the SIMT kernels of aggregate.cu (kept as a cross-check)
   const bool on = !(e && e[0] == '0');
-  return on && N >= 1 && K >= 1 && K <= 128 && D >= 16 && D % 8 == 0;
+  return on && N >= 1 && K >= 1 && K <= 128 && D >= kAtCh && D % 8 == 0;   // TMA: 16-byte row pitch, box inside the tensor
 }
 size_t assign_tc_workspace_elems(int D, int K) { return (size_t)3 * align_up((size_t)K, 16) * D; }   // bf16 elements
 

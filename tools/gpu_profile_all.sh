@@ -4,10 +4,13 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; cat gpurun_out/bench_n1.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref rc=$?"; cat gpurun_out/bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1; echo "list rc=$?"
+if [ -n "$WITH_KNN" ]; then
 timeout 900 ncu --set full --import-source on --clock-control none -k regex:'knn_tc_filter|knn_rescore|knn_refine' --launch-skip 21 --launch-count 7 \
   -f -o gpurun_out/knn_final python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-aggregation > gpurun_out/ncu_knn.log 2>&1; echo "ncu knn rc=$?"
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:'aggregate_tc_kernel|rt_planes' --launch-skip 4 --launch-count 2 \
+fi
+CALLS=3 timeout 900 ncu --set full --import-source on --clock-control none -k regex:'aggregate_tc_kernel|rt_from_tokens|assign_tc_kernel' --launch-skip 6 --launch-count 3 \
   -f -o gpurun_out/agg_final python tools/agg_run.py > gpurun_out/ncu_agg.log 2>&1; echo "ncu agg rc=$?"; tail -3 gpurun_out/ncu_agg.log
+CALLS=3 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_agg.csv python tools/agg_run.py > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
