@@ -9,7 +9,7 @@
 // 32 % of the HBM write roofline).  Here the contraction runs on tcgen05:
 //   * R is split once into three bf16 planes (hi + mid + lo = all 24 fp32 mantissa bits; the 0/1 mask is exact in bf16,
 //     so every product is exact) stored TRANSPOSED and label-sorted, RT[plane][image][d][i]: the tokens of a cluster
-//     are then a contiguous K-major column range that TMA tiles straight into the SWIZZLE_128B operand layout;
+//     are then a contiguous K-major column range that TMA tiles straight into the swizzled operand layout;
 //   * one CTA owns (image, tile of 128 segments, cluster): A = mask tile [128 x 64 tokens] written into shared memory
 //     by two builder warps from the membership words, B = [128 channels x 64 tokens] x 3 planes by TMA, D = fp32
 //     accumulators in TMEM (4 buffers of 128 columns);
@@ -141,6 +141,10 @@ int agg_tc_fused_channels(int N, int K) {
 __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // mbarrier wait that adds the cycles spent to a counter when the development probe is on
+// per-pass timeline of CTA 0 (development probe): probe[4096 + 8 * pass + j], j = 0 MMA: buffer free, 1 MMA: first operand
+// stage full, 2 MMA: pass committed, 3 producer: first stage of the pass issued, 4 epilogue (warp 2): accumulator full,
+// 5 epilogue: buffer handed back
+#define TC_MARK(ti_, j_) do { if (probe && blockIdx.x == 0 && (ti_) < 256) probe[4096 + 8 * (ti_) + (j_)] = clock64(); } while (0)
 #define TC_TIMED_WAIT(bar, par, acc) do { if (probe) { const long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
 
 struct TcItem {
@@ -311,16 +315,20 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
     // ===================== TMA producer =====================
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_rt) : "memory");
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, tp = 0;
       long long t_wait = 0;
       for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
         const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
         if (it.rows == 0) continue;
         const int n_inst = P + (it.pj1 - it.pj0);
-        for (int inst = 0; inst < n_inst; ++inst) {
+        for (int inst = 0; inst < n_inst; ++inst, ++tp) {
           const int pass = inst < P ? inst : it.pj0 + inst - P;
+          // (r1: an L2 prefetch of the operand rows 1-3 passes ahead -- the norm sweep is their first touch, ~2.9 k cycles
+          // per box from DRAM -- shortens the MMA's operand waits but costs more TMA time than it saves: 0.418 -> 0.434 /
+          // 0.442 / 0.447 ms for a look-ahead of 1 / 2 / 3 passes; profiles/r1_agg_experiments.txt)
           for (int c = 0; c < it.nch; ++c) {
             TC_TIMED_WAIT(bar_empty + 8 * stage, phase ^ 1, t_wait);
+            if (c == 0) TC_MARK(tp, 3);
             const uint32_t sb = smem_u32(smem + stage * kTcStageBytes) + kTcTileBytes;
             const uint32_t fb = bar_full + 8 * stage;
             mbar_arrive_expect_tx(fb, 3 * kTcTileBytes);
@@ -352,24 +360,30 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
           const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
           TC_TIMED_WAIT(bar_tempty + 8 * buf, (use & 1) ^ 1, t_tempty);
           tc_fence_after();
+          TC_MARK(ti, 0);
           const uint32_t d_tmem = tmem_base + buf * kTcPassN;
           for (int c = 0; c < it.nch; ++c) {
             TC_TIMED_WAIT(bar_full + 8 * stage, phase, t_full);
             tc_fence_after();
+            if (c == 0) TC_MARK(ti, 1);
             const uint32_t sa = smem_u32(smem + stage * kTcStageBytes);
+            // descriptors of the stage's tiles differ only in the (address >> 4) field: one encode, constant offsets
+            // (r1 timeline: the issuing thread, not the tensor pipe, paced the norm sweep at ~130 cycles per MMA)
             const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = adesc + (kTcTileBytes >> 4);
             const int nk = (min(kTcTokChunk, it.p1 - it.x0 - c * kTcTokChunk) + 15) >> 4;
             for (int kk = 0; kk < nk; ++kk) {
-              const uint64_t adv = (uint64_t)(kk * 32 >> 4);
-#pragma unroll
-              for (int pl = 0; pl < 3; ++pl)   // lo, mid, hi: small terms first
-                tc_mma_bf16(d_tmem, adesc + adv, umma_desc_sw128(sa + (1 + pl) * kTcTileBytes) + adv, idesc,
-                            (c | kk | pl) != 0);
+              const uint64_t adv = (uint64_t)(kk * 2);                  // 16 tokens = 32 bytes along K
+              // lo, mid, hi: small terms first
+              tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv, idesc, (c | kk) != 0);
+              tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv + (kTcTileBytes >> 4), idesc, 1u);
+              tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv + 2 * (kTcTileBytes >> 4), idesc, 1u);
             }
             tc_commit(bar_empty + 8 * stage);
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
           }
           tc_commit(bar_tfull + 8 * buf);
+          TC_MARK(ti, 2);
         }
       }
       if (probe) { probe[blockIdx.x * 16 + 6] = t_tempty; probe[blockIdx.x * 16 + 7] = t_full;
@@ -472,6 +486,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
         TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_nwait);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TC_MARK(ti, 4);
         const uint32_t tcol = tlane + buf * kTcPassN + c0;
         uint32_t va[32], vb[32];
         if (w0 > 0) {                                  // (warp-uniform)
@@ -484,6 +499,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (warp == 2 && lane == 0) TC_MARK(ti, 5);
       }
       double* xs = s_ssq + (n_done & 1) * 2 * kTcSegTile;
       xs[half * kTcSegTile + row] = ssq;
@@ -506,6 +522,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
         TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_wwait);
         tc_fence_after();
+        if (warp == 2 && lane == 0) TC_MARK(ti, 4);
         const long long t_s0 = probe ? clock64() : 0;
         const uint32_t tcol = tlane + buf * kTcPassN + c0;
         OutT* op = orow + (size_t)pass * kTcPassN + c0;
@@ -550,6 +567,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
           if (w1 > 0) TcOut<OutT>::store(op + 32, vb, sc, w1);
         }
         if (probe) t_store += clock64() - t_s0;
+        if (warp == 2 && lane == 0) TC_MARK(ti, 5);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging boxes drained before exit
