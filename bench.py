@@ -259,6 +259,45 @@ def aggregation_side_bench(device, peaks):
                          "traffic": _traffic().get("aggregate_dram_bytes_per_launch")}}
 
 
+def pca_side_bench(device, peaks):
+    """Secondary: PCA-whitening projection of one aggregation batch, 2048 SuperSegments x 49152 -> 1024
+    (the published configuration's shape), tensor-core kernel; algorithmic FLOPs = 2 * S * D_in * D_out."""
+    from revisit_anything_b200 import _lib, engine
+    lib = _lib.lib()
+    S, Din, Dout = 2048, 49152, 1024
+    g = torch.Generator(device=device).manual_seed(12)
+    X = torch.randn(S, Din, generator=g, device=device, dtype=torch.float64) / Din ** 0.5
+    W = torch.randn(Dout, Din, generator=g, device=device) / Din ** 0.5
+    mu = torch.randn(Din, generator=g, device=device, dtype=torch.float64) * 1e-3
+    ev = torch.rand(Dout, generator=g, device=device) * 1e-4 + 1e-5
+    for _ in range(2):
+        y = engine.pca_project(X, W, mu, ev, normalize_rows=True)
+    torch.cuda.synchronize()
+    lib.segvlad_profile_reset()
+    lib.segvlad_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        y = engine.pca_project(X, W, mu, ev, normalize_rows=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tot, n = C.c_double(0), C.c_int(0)
+    lib.segvlad_profile_read(4, C.byref(tot), C.byref(n))
+    lib.segvlad_profile_enable(0)
+    lib.segvlad_profile_reset()
+    kern_ms = tot.value / max(n.value, 1) if n.value else ms
+    flops = 2.0 * S * Din * Dout
+    del y
+    return {"workload": f"{S} SuperSegments x {Din} -> {Dout} (fp64 in/out), row-normalised",
+            "superseg_per_s": S / (ms * 1e-3), "ms_per_batch": ms, "kernel_ms": kern_ms,
+            "roofline": {"bound": "tensor", "achieved": flops / (kern_ms * 1e-3) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                         "unit": "TFLOP/s", "frac": flops / (kern_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                         "note": "algorithmic 2*S*D_in*D_out; the kernel issues 6 bf16 MMA products per term (fp32-equivalent "
+                                 "split operands), so tensor-pipe utilisation is 6x this fraction"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,6 +429,7 @@ def main():
     if rank == 0 and world == 1:
         if not args.no_aggregation:
             out["aggregation"] = aggregation_side_bench(device, peaks)
+            out["pca"] = pca_side_bench(device, peaks)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_quick()
     if rank == 0:

@@ -49,6 +49,7 @@ uint64_t segvlad_launch_count(void);
 #define SEGVLAD_PROF_KNN_FILTER 1 /* tcgen05 (or SIMT) all-pairs + filter kernel */
 #define SEGVLAD_PROF_AGGREGATE 2  /* masked residual aggregation kernel          */
 #define SEGVLAD_PROF_KNN_RESCORE 3
+#define SEGVLAD_PROF_PCA 4         /* tensor-core PCA projection kernel            */
 void segvlad_profile_enable(int on);
 int segvlad_profile_read(int tag, double* total_ms, int* launches); /* synchronises the recorded events */
 void segvlad_profile_reset(void);
@@ -169,6 +170,19 @@ size_t segvlad_pca_workspace_bytes(int S, int D_in, int D_out);
 int segvlad_pca_project(const double* X, int S, int D_in, const float* components, const double* mean,
                         const float* explained_variance, int D_out, int normalize_rows, double* Y,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Tensor-core version of the same projection (csrc/project_tc.cu): the components are split once per model into bf16
+ * planes (segvlad_pca_prepare_planes, planes = segvlad_pca_planes_bytes(D_in, D_out) bytes of device memory, kept by
+ * the caller next to the model -- the reference re-unpickles the model on every batch, func_vpr.py:1431-1436), the
+ * projection accumulates 512-channel chunks in fp32 on tcgen05 and the chunk sums in fp64 (~1e-6 relative, inside the
+ * 1e-5 descriptor tolerance).  segvlad_pca_tc_supported: D_in >= 64 and a multiple of 8, and SEGVLAD_PCA_TC != "0";
+ * otherwise use segvlad_pca_project (fp64 CUDA cores, also the cross-check).  X and mean must be 16-byte aligned. */
+int segvlad_pca_tc_supported(int D_in, int D_out);
+size_t segvlad_pca_planes_bytes(int D_in, int D_out);
+int segvlad_pca_prepare_planes(const float* components, int D_out, int D_in, void* planes, void* stream);
+size_t segvlad_pca_tc_workspace_bytes(int S, int D_in, int D_out);
+int segvlad_pca_project_tc(const double* X, int S, int D_in, const void* planes, const double* mean,
+                           const float* explained_variance, int D_out, int normalize_rows, double* Y,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * NetVLAD + anti-burst aggregation (BASELINE config 5; data parallel over images, no collective).

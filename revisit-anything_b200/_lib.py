@@ -40,6 +40,11 @@ _SIGS = {
                                C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "segvlad_pca_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "segvlad_pca_project": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
+    "segvlad_pca_tc_supported": (C.c_int, [C.c_int, C.c_int]),
+    "segvlad_pca_planes_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "segvlad_pca_prepare_planes": (C.c_int, [_p, C.c_int, C.c_int, _p, _p]),
+    "segvlad_pca_tc_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
+    "segvlad_pca_project_tc": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
     "segvlad_netvlad_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "segvlad_netvlad_antiburst": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, C.c_float, C.c_float,
                                             C.c_float, _p, _p, C.c_size_t, _p]),

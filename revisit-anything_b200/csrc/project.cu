@@ -82,6 +82,12 @@ pca_finalize_kernel(const double* __restrict__ part, int n_split, const float* _
   for (int o = threadIdx.x; o < Dout; o += 256) Y[(size_t)s * Dout + o] /= nrm;   // zero row -> NaN, like normalizeFeat
 }
 
+// shared with project_tc.cu: sum of the K-split partials in a fixed order, 1/sqrt(ev), optional row normalisation
+void pca_finalize_launch(const double* part, int n_split, const float* ev, int S, int Dout, int normalize_rows, double* Y,
+                         cudaStream_t st) {
+  pca_finalize_kernel<<<S, 256, 0, st>>>(part, n_split, ev, S, Dout, normalize_rows, Y);
+}
+
 static int pca_splits(int S, int Din, int Dout) {
   const long long tiles = (long long)((S + kPjTile - 1) / kPjTile) * ((Dout + kPjTile - 1) / kPjTile);
   int z = (int)((4 * 148 + tiles - 1) / tiles);   // ~4 CTAs per SM

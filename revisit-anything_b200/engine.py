@@ -287,10 +287,27 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
 # --------------------------------------------------------------------------------------------
 # PCA-whitening projection (row f1)
 # --------------------------------------------------------------------------------------------
+_PCA_PLANES = {}   # components tensor -> bf16 planes of the tensor-core projection (one model at a time)
+
+
+def _pca_planes(W: torch.Tensor) -> torch.Tensor:
+    key = (W.data_ptr(), tuple(W.shape), W._version, W.device.index)
+    ent = _PCA_PLANES.get(key)
+    if ent is None:
+        Dout, Din = W.shape
+        planes = _ws(lib().segvlad_pca_planes_bytes(Din, Dout), W.device)
+        check(lib().segvlad_pca_prepare_planes(_ptr(W), Dout, Din, _ptr(planes), _stream()), "segvlad_pca_prepare_planes")
+        _PCA_PLANES.clear()
+        ent = _PCA_PLANES[key] = (planes, W)     # W is kept alive: its address is the key
+    return ent[0]
+
+
 def pca_project(X: torch.Tensor, components: torch.Tensor, mean: torch.Tensor, explained_variance: torch.Tensor,
                 normalize_rows: bool = False) -> torch.Tensor:
-    """Y = ((X - mean) @ components^T) / sqrt(explained_variance) in fp64 (sklearn PCA.transform, whiten=True);
-    optional normalizeFeat.  X [S, D_in] CUDA (any float dtype, computed in fp64), returns [S, D_out] fp64 CUDA."""
+    """Y = ((X - mean) @ components^T) / sqrt(explained_variance) (sklearn PCA.transform, whiten=True); optional
+    normalizeFeat.  X [S, D_in] CUDA (any float dtype, read as fp64), returns [S, D_out] fp64 CUDA.  Default: tcgen05 kernel
+    (fp32-equivalent split operands, fp64 across 512-channel chunks, ~1e-6 relative); SEGVLAD_PCA_TC=0 or an unsupported
+    D_in selects the fp64 CUDA-core kernel."""
     _need_cuda(X, components, mean, explained_variance)
     X = X.contiguous().double()
     S, Din = X.shape
@@ -299,6 +316,12 @@ def pca_project(X: torch.Tensor, components: torch.Tensor, mean: torch.Tensor, e
     mu = mean.contiguous().double()
     ev = explained_variance.contiguous().float()
     Y = torch.empty((S, Dout), dtype=torch.float64, device=X.device)
+    if lib().segvlad_pca_tc_supported(Din, Dout):
+        planes = _pca_planes(W)
+        ws = _ws(lib().segvlad_pca_tc_workspace_bytes(S, Din, Dout), X.device)
+        check(lib().segvlad_pca_project_tc(_ptr(X), S, Din, _ptr(planes), _ptr(mu), _ptr(ev), Dout, int(normalize_rows),
+                                           _ptr(Y), _ptr(ws), ws.numel(), _stream()), "segvlad_pca_project_tc")
+        return Y
     ws = _ws(lib().segvlad_pca_workspace_bytes(S, Din, Dout), X.device)
     check(lib().segvlad_pca_project(_ptr(X), S, Din, _ptr(W), _ptr(mu), _ptr(ev), Dout, int(normalize_rows), _ptr(Y),
                                     _ptr(ws), ws.numel(), _stream()), "segvlad_pca_project")
