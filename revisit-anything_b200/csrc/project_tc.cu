@@ -8,13 +8,14 @@
 //     (hh, hm, mh, hl, lh, mm) are accumulated in fp32 TMEM -- the main product hh in one accumulator, the five small
 //     ones in a second (TMEM adds truncate: every accumulating MMA costs an ulp of the running sum);
 //   * fp32 accumulation only runs over CHUNKS of 512 channels (32 main MMAs per element); the chunk sums are added in
-//     fp64 in registers (thread = output row x 32 columns), so the rounding of a 49152-term sum stays at ~2e-6
-//     relative -- inside the 1e-5 descriptor tolerance of north_star (tests/test_gpu_pca.py);
+//     fp64 to accumulators that live in the other half of TMEM as (lo, hi) word pairs (tcgen05.ld / add / tcgen05.st by
+//     the thread that owns the row), so the rounding of a 49152-term sum stays at ~2e-6 relative -- inside the 1e-5
+//     descriptor tolerance of north_star (tests/test_gpu_pca.py);
 //   * CTA = 128 rows x 128 components x one K split.  X is K-major already (row = segment), so the 16 converter warps read
 //     it coalesced (512 contiguous bytes per warp and row), subtract the mean, split and write 4-byte pieces into the
 //     SWIZZLE_128B A tile (one 128-byte row per warp store: conflict-free); the component planes come by TMA; warp 0 issues
-//     24 MMAs (M=128, N=128, K=16) per 64-channel stage; two TMEM accumulator pairs alternate between chunks, the converter
-//     warps drain the finished one (four warps per TMEM lane quarter) while the next chunk's MMAs run;
+//     24 MMAs (M=128, N=128, K=16) per 64-channel stage; after every chunk the converter warps (four per TMEM lane
+//     quarter) fold the two fp32 chunk sums into the fp64 accumulators and hand them back to the MMA warp;
 //   * split K over blockIdx.z for small S; the fp64 partials are summed, scaled by 1/sqrt(ev) and optionally
 //     row-normalised by pca_finalize_kernel (project.cu) in a fixed order: deterministic.
 #include <stdlib.h>
@@ -73,6 +74,18 @@ __device__ __forceinline__ void pt_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void pt_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
 // part[z][S][Dout] (fp64) = sum over this split's channels of (X - mean) . W^T
 __global__ void __launch_bounds__(kPtThreads, 1)
 pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restrict__ X, const double* __restrict__ mean,
@@ -83,8 +96,8 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   const uint32_t bar_full = smem_u32(bars + 0);      // [stages] A written (8 converter warps) + B landed (TMA)
   const uint32_t bar_empty = smem_u32(bars + 2);     // [stages] MMAs that read the stage retired
-  const uint32_t bar_tfull = smem_u32(bars + 4);     // [2] chunk accumulator complete
-  const uint32_t bar_tempty = smem_u32(bars + 6);    // [2] chunk accumulator drained by the 8 converter warps
+  const uint32_t bar_tfull = smem_u32(bars + 4);     // chunk accumulators (main, small) complete
+  const uint32_t bar_tempty = smem_u32(bars + 6);    // chunk accumulators drained by the converter warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * kPtCols, row0 = blockIdx.y * kPtRows;
   const int n_st_total = (Din + kPtCh - 1) / kPtCh;
@@ -95,7 +108,8 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kPtStages; ++i) { mbar_init(bar_full + 8 * i, kPtConv + 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, kPtConv); }
+    mbar_init(bar_tfull, 1);
+    mbar_init(bar_tempty, kPtConv);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -133,10 +147,9 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
       // truncation errors are 2^-8 smaller; both are added in fp64 when the chunk is drained.
       const int pa[5] = {0, 2, 1, 1, 2}, pb[5] = {2, 0, 1, 2, 1};
       for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t buf = c & 1, cuse = c >> 1;
-        mbar_wait(bar_tempty + 8 * buf, (cuse & 1) ^ 1);
+        mbar_wait(bar_tempty, (c & 1) ^ 1);                 // the previous chunk has been added to the fp64 accumulators
         tc_fence_after();
-        const uint32_t d_main = tmem_base + buf * 2 * kPtCols, d_small = d_main + kPtCols;
+        const uint32_t d_main = tmem_base, d_small = tmem_base + kPtCols;
         const int cs0 = c * kPtChunk, cs1 = min(n_st, cs0 + kPtChunk);
         for (int s = cs0; s < cs1; ++s) {
           const int stage = s % kPtStages, use = s / kPtStages;
@@ -155,7 +168,7 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
           }
           tc_commit(bar_empty + 8 * stage);
         }
-        tc_commit(bar_tfull + 8 * buf);
+        tc_commit(bar_tfull);
       }
     }
   } else {
@@ -163,27 +176,42 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
     const int cw = warp - 2;                               // 0 .. 15: rows cw, cw + 16, ... of the tile
     const int quarter = warp & 3, cpart = cw >> 2;         // TMEM lane quarter of this warp, 32-column part
     const int orow = quarter * 32 + lane;                  // output row of this thread within the tile
-    double acc[32];
+    // TMEM columns: [0,128) main fp32 chunk sum, [128,256) small-product fp32 chunk sum, [256,512) the fp64 accumulators of
+    // the tile as (lo, hi) word pairs -- they live in tensor memory because 32 doubles per thread next to the converter
+    // state spilled (ncu: 12 GB of local-memory traffic per call with register accumulators)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_acc = t_lane + 2 * kPtCols + cpart * 64;
+    {
+      uint32_t z[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-    auto drain = [&](int c) {                              // chunk c: TMEM (fp32, main + small) -> += fp64 registers
-      const uint32_t buf = c & 1, cuse = c >> 1;
-      mbar_wait(bar_tfull + 8 * buf, cuse & 1);
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+      pt_st32(t_acc, z);
+      pt_st32(t_acc + 32, z);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    auto drain = [&](int c) {                              // chunk c: fp64 accumulators += main + small (fp32)
+      mbar_wait(bar_tfull, c & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * 2 * kPtCols + cpart * 32;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t v[16];
-        pt_ld16(taddr + kPtCols + 16 * h, v);              // small products first
+        uint32_t vm[16], vs[16], aw[32];
+        pt_ld16(t_lane + cpart * 32 + 16 * h, vm);
+        pt_ld16(t_lane + kPtCols + cpart * 32 + 16 * h, vs);
+        tc_ld32(t_acc + 32 * h, aw);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[16 * h + j] += (double)__uint_as_float(v[j]);
-        pt_ld16(taddr + 16 * h, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[16 * h + j] += (double)__uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) {
+          double a = __hiloint2double((int)aw[2 * j + 1], (int)aw[2 * j]);
+          a += (double)__uint_as_float(vs[j]);             // small products first
+          a += (double)__uint_as_float(vm[j]);
+          aw[2 * j] = (uint32_t)__double2loint(a);
+          aw[2 * j + 1] = (uint32_t)__double2hiint(a);
+        }
+        pt_st32(t_acc + 32 * h, aw);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      if (lane == 0) mbar_arrive(bar_tempty);
     };
     for (int s = 0; s < n_st; ++s) {
       const int stage = s % kPtStages, use = s / kPtStages;
@@ -191,15 +219,20 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
       const bool dok = d < Din;                            // Din is even (multiple of 8)
       double2 mu = make_double2(0.0, 0.0);
       if (dok) mu = *reinterpret_cast<const double2*>(mean + d);
+      // When the slot frees, the MMAs of stage s - 2 have retired: if that was the last stage of a chunk, its sums are
+      // complete and are folded in first (before this stage's loads, so that their registers are not live across it)
+      const bool fold = s >= 2 && (s - 1) % kPtChunk == 0;
+      if (fold) {
+        mbar_wait(bar_empty + 8 * stage, (use & 1) ^ 1);
+        drain((s - 2) / kPtChunk);
+      }
       double2 x[8];                                        // issued before the slot wait: in flight while the MMAs retire
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = row0 + cw + kPtConv * i;
         x[i] = (dok && r < S) ? __ldg(reinterpret_cast<const double2*>(X + (size_t)r * Din + d)) : mu;
       }
-      mbar_wait(bar_empty + 8 * stage, (use & 1) ^ 1);
-      // the MMAs of stage s - 2 have retired: if that was the last stage of a chunk, its accumulator is complete
-      if (s >= 2 && (s - 1) % kPtChunk == 0) drain((s - 2) / kPtChunk);
+      if (!fold) mbar_wait(bar_empty + 8 * stage, (use & 1) ^ 1);
       const uint32_t sa = smem_u32(smem + stage * kPtStageBytes);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -222,16 +255,15 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
     for (int c = 0; c < n_chunks; ++c)
       if ((c + 1) * kPtChunk + 1 > n_st - 1) drain(c);
     const int r = row0 + orow;
-    if (r < S) {
-      double* o = part + ((size_t)blockIdx.z * S + r) * Dout + n0 + cpart * 32;
-      if ((Dout & 1) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2)
-          if (n0 + cpart * 32 + j < Dout) *reinterpret_cast<double2*>(o + j) = make_double2(acc[j], acc[j + 1]);
-      } else {           // odd row length: rows are only 8-byte aligned
+    for (int h = 0; h < 2; ++h) {
+      uint32_t aw[32];
+      tc_ld32(t_acc + 32 * h, aw);                         // (warp-collective: executed by every lane)
+      if (r < S) {
+        double* o = part + ((size_t)blockIdx.z * S + r) * Dout + n0 + cpart * 32 + 16 * h;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + cpart * 32 + j < Dout) o[j] = acc[j];
+        for (int j = 0; j < 16; ++j)
+          if (n0 + cpart * 32 + 16 * h + j < Dout) o[j] = __hiloint2double((int)aw[2 * j + 1], (int)aw[2 * j]);
       }
     }
   }

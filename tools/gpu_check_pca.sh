@@ -8,7 +8,5 @@ import bench
 peaks, _ = bench._peaks()
 r = bench.pca_side_bench(torch.device('cuda'), peaks)
 print('tc  ', json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k != 'roofline'}), round(r['roofline']['achieved'], 1), 'TFLOP/s algorithmic')
-os.environ['SEGVLAD_PCA_TC'] = '0'
-r = bench.pca_side_bench(torch.device('cuda'), peaks)
-print('fp64', json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items() if k != 'roofline'}))
 PY
+bash tools/gpu_ncu_pca_quick.sh
