@@ -373,12 +373,15 @@ def main():
         step_resident()
     lib.segvlad_profile_reset()
     lib.segvlad_profile_enable(1)
+    # clocks are sampled on a host thread through both timed regions (resident steps, then end-to-end steps); a short GIL
+    # switch interval keeps the sampler alive while the main thread enqueues launches
+    old_switch = sys.getswitchinterval()
+    sys.setswitchinterval(2e-4)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = lib.segvlad_launch_count()
     ms_total = timed(step_resident, args.steps)
     launches = lib.segvlad_launch_count() - l0
-    clocks = sampler.stop()
     tot, n = C.c_double(0), C.c_int(0)
     lib.segvlad_profile_read(1, C.byref(tot), C.byref(n))
     tc_ms, tc_launches = tot.value, n.value
@@ -390,6 +393,8 @@ def main():
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    sys.setswitchinterval(old_switch)
 
     pairs_step = NQ * NR_PER_GPU * world
     ms_step = ms_total / args.steps

@@ -5,7 +5,8 @@
 // kernel (aggregate.cu: split-K register tiles + finalize) runs it at ~20 TFLOP/s (r1 launch list: 248 + 74 us, a third of
 // the batch).  Here it runs on tcgen05 with fp32-equivalent operands: x and c_hat are split into three bf16 pieces
 // (hi + mid + lo = all 24 mantissa bits) and the six products down to 2^-16 (hh, hm, mh, hl, lh, mm) are accumulated in
-// fp32 TMEM, small terms first -- the dropped terms are <= 2^-23 relative, the rounding level of the reference's SGEMM.
+// fp32 TMEM (hh and the five small ones in separate accumulators) -- the dropped terms are <= 2^-23 relative, the rounding
+// level of the reference's SGEMM.
 //   * CTA = (image, 128 tokens).  The tokens arrive channel-major, so the A operand (tokens x channels, K-major) is
 //     written by 8 converter warps: coalesced LDG along the tokens, split, 16-byte st.shared into the SWIZZLE_128B
 //     layout (thread = token row: conflict-free), ||x||^2 accumulated on the way.
@@ -144,15 +145,19 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + 3 * kAtATile;
-        // planes: 0 = lo, 1 = mid, 2 = hi.  Products from small to large: (l,h) (h,l) (m,m) (m,h) (h,m) (h,h)
-        const int pa[6] = {0, 2, 1, 1, 2, 2}, pb[6] = {2, 0, 1, 2, 1, 2};
+        // planes: 0 = lo, 1 = mid, 2 = hi.  TMEM adds truncate (every accumulating MMA costs up to an ulp of the running
+        // sum, csrc/project_tc.cu): the main product (h,h) has its own accumulator (D/16 MMAs), the five small ones --
+        // (l,h) (h,l) (m,m) (m,h) (h,m), 2^-8 of the sum -- share a second one at columns [Kp, 2 Kp); added in the epilogue
+        const int pa[5] = {0, 2, 1, 1, 2}, pb[5] = {2, 0, 1, 2, 1};
 #pragma unroll
         for (int kk = 0; kk < kAtCh / 16; ++kk) {
           const uint64_t adv = (uint64_t)(kk * 32 >> 4);
 #pragma unroll
-          for (int q = 0; q < 6; ++q)
-            tc_mma_bf16(tmem_base, umma_desc_sw128(sa + pa[q] * kAtATile) + adv, umma_desc_sw128(sb + pb[q] * btile) + adv,
+          for (int q = 0; q < 5; ++q)
+            tc_mma_bf16(tmem_base + Kp, umma_desc_sw128(sa + pa[q] * kAtATile) + adv, umma_desc_sw128(sb + pb[q] * btile) + adv,
                         idesc, (s | kk | q) != 0);
+          tc_mma_bf16(tmem_base, umma_desc_sw128(sa + 2 * kAtATile) + adv, umma_desc_sw128(sb + 2 * btile) + adv, idesc,
+                      (s | kk) != 0);
         }
         tc_commit(bar_empty + 8 * stage);
       }
@@ -208,11 +213,12 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
       float bestv = -INFINITY;
       int besti = 0;
       for (int c0 = 0; c0 < Kp; c0 += 16) {
-        uint32_t v[16];
+        uint32_t v[16], w[16];
         tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, v);
+        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + Kp + c0, w);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float f = __uint_as_float(v[j]);
+          const float f = __uint_as_float(v[j]) + __uint_as_float(w[j]);
           if (c0 + j < K && f > bestv) { bestv = f; besti = c0 + j; }
         }
       }
@@ -255,7 +261,7 @@ int assign_tc_run(const float* tokens, int B, int N, int D, const float* centers
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (centres) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
   int tmem_cols = 32;
-  while (tmem_cols < Kp) tmem_cols *= 2;
+  while (tmem_cols < 2 * Kp) tmem_cols *= 2;   // main + small-product accumulators
   const size_t smem = assign_tc_smem(Kp);
   SV_CHECK_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   assign_tc_kernel<<<dim3((N + kAtTok - 1) / kAtTok, B), kAtThreads, smem, st>>>(map, tokens, N, D, K, Kp, tmem_cols, prenorm,
