@@ -78,21 +78,22 @@ def test_pack_roundtrip():
         D.pack_topk(d2, torch.tensor([[2 ** 31, 0, 0]], dtype=torch.int64))
 
 
-def test_world2_gloo_matches_single_process():
+@pytest.mark.parametrize("world,k", [(2, 64), (4, 80)])
+def test_world2_gloo_matches_single_process(world, k):
+    # world 4: uneven shards (75, 75, 75, 74 rows), each SHORTER than k = 80 -> padded (+inf, -1) lists enter the merge
     q, r, imq, imr = synth.make_structured_bank(n_ref_img=23, n_qry_img=6, segs_per_img=13, D=48, seed=3, noise=1.0)
     r[40] = r[200]                                    # an exact cross-shard tie: merge must keep idx order
-    k = 64
     imq_off = torch.from_numpy(np.arange(0, 6 * 13 + 1, 13).astype(np.int32))
     imr_t = torch.from_numpy(imr)
     mgr = mp.Manager()
     out = mgr.dict()
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, q, r, imq_off, imr_t, k, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, q, r, imq_off, imr_t, k, out), nprocs=world, join=True)
     D2, I = O.flat_l2_search(q.numpy(), r.numpy(), k)
     sims, matches = O.sims_from_d2(D2, I, 50)
     rng = [np.arange(i * 13, (i + 1) * 13) for i in range(6)]
     preds = [list(map(int, p)) for p in O.get_matches_wt_borda(matches, 6, sims, rng, imr, n=5)]
-    for rank in (0, 1):
+    for rank in range(world):
         d2, idx, p = out[rank]
         np.testing.assert_array_equal(d2, D2)
         np.testing.assert_array_equal(idx, I)

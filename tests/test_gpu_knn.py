@@ -115,6 +115,27 @@ def test_merge_topk_matches_single_shard():
     np.testing.assert_array_equal(mi.cpu().numpy(), idx_full)
 
 
+def test_merge_topk_with_shards_shorter_than_k():
+    # a shard with fewer rows than k returns (+inf, -1) padded lists (like faiss); the merge must skip the padding, and a
+    # bank with fewer than k rows in total stays padded after the merge
+    q, r = synth.make_descriptor_bank(130, 700, 128, seed=9, planted=20, device=DEV)
+    k = 200
+    qb = engine.Bank.prepare(q)
+    for bounds in ([0, 60, 150, 700], [0, 50, 120, 180]):
+        n = bounds[-1]
+        d2_full, idx_full = _run_tc(q, r[:n], k)
+        parts_d, parts_i = [], []
+        for g in range(3):
+            d, i = engine.knn(qb, engine.Bank.prepare(r[bounds[g]:bounds[g + 1]]), k, row_offset=bounds[g])
+            parts_d.append(d)
+            parts_i.append(i)
+        md, mi = engine.merge_topk(torch.stack(parts_d), torch.stack(parts_i))
+        np.testing.assert_array_equal(md.cpu().numpy(), d2_full)
+        np.testing.assert_array_equal(mi.cpu().numpy(), idx_full)
+        if n < k:
+            assert (mi.cpu().numpy()[:, n:] == -1).all() and np.isinf(md.cpu().numpy()[:, n:]).all()
+
+
 def test_bank_prepare_f64_normalizes_like_normalizeFeat():
     g = torch.Generator().manual_seed(3)
     x = torch.randn(500, 200, generator=g, dtype=torch.float64) * 3.0
