@@ -282,11 +282,20 @@ void pca_finalize_launch(const double* part, int n_split, const float* ev, int S
 static int pca_tc_splits(int S, int Din, int Dout, int* stages_per_split) {
   const int n_st = (Din + kPtCh - 1) / kPtCh;
   const long long tiles = (long long)((S + kPtRows - 1) / kPtRows) * ((Dout + kPtCols - 1) / kPtCols);
-  int z = (int)((148 + tiles - 1) / tiles);                 // one CTA per SM (192 KB of shared memory each)
   int zmax = n_st / (2 * kPtChunk);                         // >= two accumulation chunks per split
   if (zmax < 1) zmax = 1;
-  if (z > zmax) z = zmax;
-  int sps = (n_st + z - 1) / z;
+  if (zmax > 16) zmax = 16;                                 // bounds the fp64 partials (z x S x Dout x 8 bytes)
+  // one CTA per SM (192 KB of shared memory each): take the smallest K split whose last wave is at least 95 % full,
+  // else the best one (2048 x 1024: 128 tiles -> z = 8, 1024 CTAs = 6.9 waves instead of 1.7)
+  int best_z = 1;
+  double best_eff = 0.0;
+  for (int z = 1; z <= zmax; ++z) {
+    const long long ctas = tiles * z, waves = (ctas + 147) / 148;
+    const double eff = (double)ctas / (double)(waves * 148);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_z = z; }
+    if (eff >= 0.95) { best_z = z; break; }
+  }
+  int sps = (n_st + best_z - 1) / best_z;
   sps = (sps + kPtChunk - 1) / kPtChunk * kPtChunk;
   *stages_per_split = sps;
   return (n_st + sps - 1) / sps;
