@@ -103,6 +103,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, p0 = blockIdx.x * kAtTok;
   const int n_st = (D + kAtCh - 1) / kAtCh;
+  const bool stacked = 6 * Kp <= 512;          // every product in its own TMEM columns (three wide MMAs per k-step)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAtStages; ++i) { mbar_init(bar_full + 8 * i, 9); mbar_init(bar_empty + 8 * i, 1); }
@@ -146,18 +147,37 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + 3 * kAtATile;
         // planes: 0 = lo, 1 = mid, 2 = hi.  TMEM adds truncate (every accumulating MMA costs up to an ulp of the running
-        // sum, csrc/project_tc.cu): the main product (h,h) has its own accumulator (D/16 MMAs), the five small ones --
-        // (l,h) (h,l) (m,m) (m,h) (h,m), 2^-8 of the sum -- share a second one at columns [Kp, 2 Kp); added in the epilogue
-        const int pa[5] = {0, 2, 1, 1, 2}, pb[5] = {2, 0, 1, 2, 1};
+        // sum, csrc/project_tc.cu), so the main product (h,h) never shares an accumulator with the small ones.
+        if (stacked) {
+          // The three c_hat planes of a stage are consecutive K-major row blocks: ONE MMA per token piece covers several
+          // of them (x_hi . [lo | mid | hi] with N = 3 Kp, x_mid . [mid | hi] with N = 2 Kp, x_lo . [hi] with N = Kp) --
+          // three MMAs per k-step instead of six (the small N = Kp MMAs are latency-bound, ~125 cycles each), every
+          // product in its own accumulator columns: [0,3Kp) = hl hm hh, [3Kp,5Kp) = mm mh, [5Kp,6Kp) = lh.
+          const uint32_t ibase = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kAtTok >> 4) << 24);
 #pragma unroll
-        for (int kk = 0; kk < kAtCh / 16; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+          for (int kk = 0; kk < kAtCh / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+            const uint32_t acc = (s | kk) != 0;
+            tc_mma_bf16(tmem_base + 5 * Kp, umma_desc_sw128(sa) + adv, umma_desc_sw128(sb + 2 * btile) + adv,
+                        ibase | ((uint32_t)(Kp >> 3) << 17), acc);
+            tc_mma_bf16(tmem_base + 3 * Kp, umma_desc_sw128(sa + kAtATile) + adv, umma_desc_sw128(sb + btile) + adv,
+                        ibase | ((uint32_t)(2 * Kp >> 3) << 17), acc);
+            tc_mma_bf16(tmem_base, umma_desc_sw128(sa + 2 * kAtATile) + adv, umma_desc_sw128(sb) + adv,
+                        ibase | ((uint32_t)(3 * Kp >> 3) << 17), acc);
+          }
+        } else {
+          // many clusters (6 Kp > 512 TMEM columns): (h,h) in [0,Kp), the five small products chained in [Kp,2Kp)
+          const int pa[5] = {0, 2, 1, 1, 2}, pb[5] = {2, 0, 1, 2, 1};
 #pragma unroll
-          for (int q = 0; q < 5; ++q)
-            tc_mma_bf16(tmem_base + Kp, umma_desc_sw128(sa + pa[q] * kAtATile) + adv, umma_desc_sw128(sb + pb[q] * btile) + adv,
-                        idesc, (s | kk | q) != 0);
-          tc_mma_bf16(tmem_base, umma_desc_sw128(sa + 2 * kAtATile) + adv, umma_desc_sw128(sb + 2 * btile) + adv, idesc,
-                      (s | kk) != 0);
+          for (int kk = 0; kk < kAtCh / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 32 >> 4);
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+              tc_mma_bf16(tmem_base + Kp, umma_desc_sw128(sa + pa[q] * kAtATile) + adv, umma_desc_sw128(sb + pb[q] * btile) + adv,
+                          idesc, (s | kk | q) != 0);
+            tc_mma_bf16(tmem_base, umma_desc_sw128(sa + 2 * kAtATile) + adv, umma_desc_sw128(sb + 2 * btile) + adv, idesc,
+                        (s | kk) != 0);
+          }
         }
         tc_commit(bar_empty + 8 * stage);
       }
@@ -213,12 +233,31 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restr
       float bestv = -INFINITY;
       int besti = 0;
       for (int c0 = 0; c0 < Kp; c0 += 16) {
+        const uint32_t tl = tmem_base + ((uint32_t)(quarter * 32) << 16) + c0;
         uint32_t v[16], w[16];
-        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + c0, v);
-        tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + Kp + c0, w);
+        float sm[16];
+        if (stacked) {            // small products first: (hl + lh + mm) + (hm + mh), then hh
+          tc_ld16(tl, v);                      // hl
+          tc_ld16(tl + 5 * Kp, w);             // lh
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sm[j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+          tc_ld16(tl + 3 * Kp, v);             // mm
+          tc_ld16(tl + Kp, w);                 // hm
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sm[j] += __uint_as_float(v[j]);
+          tc_ld16(tl + 4 * Kp, v);             // mh
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sm[j] += __uint_as_float(w[j]) + __uint_as_float(v[j]);
+          tc_ld16(tl + 2 * Kp, v);             // hh
+        } else {
+          tc_ld16(tl, v);
+          tc_ld16(tl + Kp, w);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sm[j] = __uint_as_float(w[j]);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float f = __uint_as_float(v[j]) + __uint_as_float(w[j]);
+          const float f = __uint_as_float(v[j]) + sm[j];
           if (c0 + j < K && f > bestv) { bestv = f; besti = c0 + j; }
         }
       }
@@ -261,7 +300,7 @@ int assign_tc_run(const float* tokens, int B, int N, int D, const float* centers
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (centres) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
   int tmem_cols = 32;
-  while (tmem_cols < 2 * Kp) tmem_cols *= 2;   // main + small-product accumulators
+  while (tmem_cols < (6 * Kp <= 512 ? 6 * Kp : 2 * Kp)) tmem_cols *= 2;   // six product accumulators, or main + small
   const size_t smem = assign_tc_smem(Kp);
   SV_CHECK_CUDA(cudaFuncSetAttribute(assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   assign_tc_kernel<<<dim3((N + kAtTok - 1) / kAtTok, B), kAtThreads, smem, st>>>(map, tokens, N, D, K, Kp, tmem_cols, prenorm,
