@@ -183,8 +183,26 @@ def anyloc_case(ref):
     print("anyloc_recall", recall)
 
 
+def netvlad_case(name="netvlad_antiburst"):
+    """a9: the reference's NetVLAD.forward with anti-burst weighting (VLAD-BuFF/models/aggregators/aggregation.py:266-361,
+    getWeights :148-162), per-cluster loop branch, CPU fp32; includes a burst (repeated tokens) and non-default ab params."""
+    mod = ref_shim.load_netvlad_module()
+    g = torch.Generator().manual_seed(31)
+    B, D, H, K = 2, 96, 9, 32
+    x = torch.randn(B, D, H, H, generator=g)
+    x[:, :, 0, :3] = x[:, :, 0, :1]
+    cent = torch.rand(K, D, generator=g)                          # aggregation.py:216 init
+    W = 12.0 * cent / cent.norm(dim=1, keepdim=True)               # init_params-style alpha * c_hat (:245-256)
+    outs = {}
+    for tag, ab in (("default", (8.0, 7.0, 1.0)), ("alt", (5.0, 3.0, 0.5))):
+        outs["out_" + tag] = ref_shim.netvlad_reference_forward(mod, x, cent, W, ab).numpy()
+        outs["ab_" + tag] = np.asarray(ab, dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x.numpy(), centroids=cent.numpy(), conv_weight=W.numpy(), **outs)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    netvlad_case()
     ref = ref_shim.load()
     anyloc_case(ref)
     seg_vlad_img, _ = _cpu_patched(ref)

@@ -86,3 +86,43 @@ def vlad_single_cpu(ref, query_descs, c_centers, masks, adj_mat=None):
     out, _ = ref.vlad_matmuls_per_cluster(c_centers.shape[0], masks.double(), res.double(), labels,
                                           adjMat=adj, device="cpu")
     return out, labels
+
+
+def load_netvlad_module():
+    """The UNMODIFIED VLAD-BuFF/models/aggregators/aggregation.py (NetVLAD + anti-burst, row a9), imported on the CPU with
+    its absent third-party imports (faiss, tqdm if missing) stubbed; used to pin oracle.netvlad_antiburst."""
+    import importlib.util
+    if not os.path.isfile(os.path.join(REF_ROOT, "VLAD-BuFF", "models", "aggregators", "aggregation.py")):
+        raise RuntimeError("reference VLAD-BuFF not mounted")
+    for name in ("faiss", "tqdm"):
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = MagicMock()
+    spec = importlib.util.spec_from_file_location(
+        "ref_vladbuff_aggregation", os.path.join(REF_ROOT, "VLAD-BuFF", "models", "aggregators", "aggregation.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def netvlad_reference_forward(mod, x_bdhw, centroids, conv_weight, ab_params=(8.0, 7.0, 1.0), for_loop_alt=False):
+    """Runs the reference's NetVLAD.forward (aggregation.py:266-361) with antiburst=True and the evaluation defaults
+    (eval.py:384-386: ab_w, ab_b, ab_p = 8, 7, 1; ab_relu / ab_inv / ab_soft off; no nv_pca), centroids and the 1x1-conv weight
+    set the way init_params does (:245-256).  `for_loop_alt` selects the broadcast branch (:346-349) instead of the per-cluster
+    loop (:351-358); both are the same arithmetic."""
+    import types
+
+    import torch
+    K, D = centroids.shape
+    args = types.SimpleNamespace(
+        expName="pin", nv_pca=None, nv_pca_alt=False, nv_pca_alt_mlp=False, antiburst=True, ab_w=float(ab_params[0]),
+        ab_b=float(ab_params[1]), ab_p=float(ab_params[2]), ab_fixed=True, ab_gen=0, ab_t=None, ab_kp=None, ab_testOnly=False,
+        ab_wOnly=False, ab_relu=False, ab_inv=False, ab_soft=False, forLoopAlt=bool(for_loop_alt), storeSAB=False)
+    net = mod.NetVLAD(clusters_num=K, dim=D, normalize_input=True, work_with_tokens=False, args=args)
+    with torch.no_grad():
+        net.centroids = torch.nn.Parameter(centroids.clone().float())
+        net.conv.weight = torch.nn.Parameter(conv_weight.clone().float().reshape(K, D, 1, 1))
+        net.conv.bias = None
+        net.eval()
+        return net(x_bdhw.float())

@@ -141,3 +141,16 @@ def test_anyloc_recall_and_map_match_reference(golden_dir):
     np.testing.assert_allclose([O.calculate_ap(r) for r in qr], g["ap"], rtol=0, atol=1e-15)
     assert abs(O.calculate_map(qr) - float(g["map"])) < 1e-15
     assert O.calculate_map([]) == 0 and O.calculate_ap([False, False]) == 0
+
+
+def test_netvlad_antiburst_matches_reference(golden_dir):
+    """a9: golden vectors from the reference's own NetVLAD.forward (anti-burst on, evaluation defaults and a second set of
+    ab parameters); the oracle restatement is bit-identical on the CPU."""
+    g = _load(golden_dir, "netvlad_antiburst")
+    x = torch.from_numpy(g["x"])
+    B, D = x.shape[:2]
+    for tag in ("default", "alt"):
+        got = O.netvlad_antiburst(x.reshape(B, D, -1), torch.from_numpy(g["centroids"]), torch.from_numpy(g["conv_weight"]),
+                                  tuple(float(v) for v in g["ab_" + tag]))
+        np.testing.assert_allclose(got.numpy(), g["out_" + tag], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(np.linalg.norm(got.numpy(), axis=1), 1.0, atol=1e-6)

@@ -49,3 +49,18 @@ def test_vote_vs_reference(ref, seed):
     got = O.get_matches_wt_borda(matches, n_qimg, sims, seg_range, im_inds_ref, n=5)
     assert [list(map(int, p)) for p in got] == [list(map(int, p)) for p in want]
     assert O.calc_recall(got, gt, 5) == ref.calc_recall(want, gt, 5)
+
+
+@pytest.mark.parametrize("B,D,H,K,ab,alt", [(2, 64, 7, 16, (8.0, 7.0, 1.0), False), (1, 128, 11, 64, (8.0, 7.0, 1.0), True),
+                                            (3, 48, 5, 8, (4.0, 2.5, 0.7), False)])
+def test_netvlad_antiburst_vs_reference(B, D, H, K, ab, alt):
+    """a9: oracle vs the reference's NetVLAD.forward (aggregation.py:266-361) imported live, both vlad branches."""
+    mod = ref_shim.load_netvlad_module()
+    g = torch.Generator().manual_seed(B * 100 + D + K)
+    x = torch.randn(B, D, H, H, generator=g)
+    x[:, :, 1, :4] = x[:, :, 1, :1]                                # a burst
+    cent = torch.rand(K, D, generator=g)
+    W = 9.0 * cent / cent.norm(dim=1, keepdim=True)
+    want = ref_shim.netvlad_reference_forward(mod, x, cent, W, ab, for_loop_alt=alt)
+    got = O.netvlad_antiburst(x.reshape(B, D, -1), cent, W, ab)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=1e-7)
