@@ -64,3 +64,31 @@ def test_netvlad_antiburst_vs_reference(B, D, H, K, ab, alt):
     want = ref_shim.netvlad_reference_forward(mod, x, cent, W, ab, for_loop_alt=alt)
     got = O.netvlad_antiburst(x.reshape(B, D, -1), cent, W, ab)
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("seed,n_comp,Din", [(0, 16, 64), (1, 40, 128)])
+def test_pca_apply_vs_reference(ref, tmp_path, seed, n_comp, Din):
+    """a5: oracle vs the reference's apply_pca_transform_from_pkl (func_vpr.py:1419-1443) on a freshly fitted whitening PCA,
+    plus normalizeFeat (:1673-1676).  The installed sklearn (1.9) applies the mean as an fp32 bias; the oracle follows the
+    reference's pinned 1.3.2 formula in fp64 -- 2e-5 relative / 5e-8 absolute covers the difference (see test_oracle_golden)."""
+    import pickle
+
+    from sklearn.decomposition import PCA
+    rng = np.random.RandomState(seed)
+    train = (rng.randn(400, Din) @ rng.randn(Din, Din) * 0.05).astype(np.float32)
+    pca = PCA(n_components=n_comp, whiten=True, svd_solver="arpack").fit(train)
+    path = tmp_path / "pca.pkl"
+    with open(path, "wb") as fh:
+        pickle.dump(pca, fh)
+    X = rng.randn(23, Din) * 0.05
+    want = ref.apply_pca_transform_from_pkl(torch.from_numpy(X), str(path)).numpy()
+    got = O.pca_apply(X, pca.mean_, pca.components_, pca.explained_variance_)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=5e-8)
+    np.testing.assert_allclose(O.normalize_feat(got), ref.normalizeFeat(want.copy()), rtol=2e-5, atol=5e-8)
+
+
+@pytest.mark.parametrize("S,order,seed", [(25, 3, 7), (9, 2, 8), (4, 1, 9), (3, 3, 10), (2, 2, 11), (1, 1, 12)])
+def test_adjacency_vs_reference(ref, S, order, seed):
+    """a4: SuperSegment adjacency (Delaunay neighbours to the given order, func_vpr.py:1309-1347) incl. the S <= 3 special case."""
+    masks = synth.make_masks(S, 48, 64, seed)
+    np.testing.assert_array_equal(O.neighbour_adjacency(masks, order), ref.nbrMasksAGGFastSingle(masks, order).numpy())
