@@ -147,6 +147,10 @@ int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, i
  *  matches [Nq, ld] int64 (first k_vote columns used), sims [Nq, ld] fp32 (or d2 if sims_is_d2 != 0:
  *  sims = 2 - d2 in fp32, place_rec_main.py:78-81)
  *  qimg_offsets [n_qimg+1] int32: query image i owns rows [off[i], off[i+1])  (segRangeQuery)
+ *  qrow_index   optional [off[n_qimg]] int32: position p of the concatenated segRangeQuery lists reads row
+ *               qrow_index[p] of matches / sims (NULL: identity, the contiguous ranges place_rec_main.py:354-355
+ *               builds).  The min / max normalisation is always taken over ALL Nq rows, like np.min / np.max over the
+ *               whole sims array at func_vpr.py:211-212; padding entries (match < 0) are excluded from it.
  *  rseg_to_rimg [Nr] int32 (imIndsRef)
  *  preds        [n_qimg, n_pred] int32 ref-image ids, -1 padded;  pred_scores [n_qimg, n_pred] fp64
  *  scores_dense / counts_dense: optional [n_qimg, n_rimg] fp64 / int32 (NULL to skip)
@@ -154,7 +158,7 @@ int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, i
  */
 size_t segvlad_vote_workspace_bytes(int Nq, int k_vote, int n_qimg, int max_segs_per_qimg);
 int segvlad_vote(const int64_t* matches, const float* sims, int ld, int sims_is_d2, int k_vote, int Nq,
-                 const int32_t* qimg_offsets, int n_qimg, int max_segs_per_qimg,
+                 const int32_t* qimg_offsets, const int32_t* qrow_index, int n_qimg, int max_segs_per_qimg,
                  const int32_t* rseg_to_rimg, int Nr, int n_rimg, int n_pred, int32_t* preds,
                  double* pred_scores, double* scores_dense, int32_t* counts_dense, float* minmax_out,
                  void* workspace, size_t workspace_bytes, void* stream);

@@ -36,7 +36,7 @@ _SIGS = {
     "segvlad_knn_debug_approx": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_size_t, _p]),
     "segvlad_merge_topk": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
     "segvlad_vote_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
-    "segvlad_vote": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, C.c_int, _p, C.c_int, C.c_int,
+    "segvlad_vote": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, C.c_int, _p, C.c_int, C.c_int,
                                C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),
     "segvlad_pca_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "segvlad_pca_project": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),

@@ -18,9 +18,11 @@
 //     r1: 256-byte bulk stores through a staging buffer were bound by the TMA request rate, ~6 k requests per item).
 //     The tensor work is ~10 % of the write time, the operand re-read comes from L2;
 //   * thread = segment row (TMEM lane), so norms and scales never leave the thread: no reductions, no CTA barriers.
-// Accumulation is fp32 in TMEM (truncating adds, measured ~4e-8 relative per MMA): <= 3 * n_k / 16 MMAs per element,
-// i.e. ~1e-6 relative for the largest clusters -- inside the 1e-5 descriptor tolerance; the planes are accumulated
-// small-to-large.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-5 and 8-11 epilogue (two warps per TMEM
+// Accumulation is fp32 in TMEM (truncating adds, measured ~4e-8..6e-8 relative per MMA).  The length of one accumulator
+// chain is bounded (kTcSubChunks chunks = 128 tokens = 24 MMAs, <= 2.9e-6 relative): a cluster with more tokens -- a
+// sky / road dominated image, the whole-image AnyLoc VLAD -- is accumulated as several chains in successive TMEM buffers
+// whose partial sums the epilogue adds in registers (fp32 round-to-nearest), so the error does not grow with n_k and
+// stays inside the 1e-5 descriptor tolerance for any vocabulary; the planes are accumulated small-to-large.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-5 and 8-11 epilogue (two warps per TMEM
 // lane quarter, 64 channels of a pass each), 6-7 mask-tile builders.
 #include "aggregate_tc.cuh"
 
@@ -144,8 +146,8 @@ __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.prox
 // per-pass timeline of CTA 0 (development probe): probe[4096 + 8 * pass + j], j = 0 MMA: buffer free, 1 MMA: first operand
 // stage full, 2 MMA: pass committed, 3 producer: first stage of the pass issued, 4 epilogue (warp 2): accumulator full,
 // 5 epilogue: buffer handed back
-#define TC_MARK(ti_, j_) do { if (probe && blockIdx.x == 0 && (ti_) < 256) probe[4096 + 8 * (ti_) + (j_)] = clock64(); } while (0)
-#define TC_TIMED_WAIT(bar, par, acc) do { if (probe) { const long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
+#define TC_MARK(ti_, j_) do { if (kProbe && probe && blockIdx.x == 0 && (ti_) < 256) probe[4096 + 8 * (ti_) + (j_)] = clock64(); } while (0)
+#define TC_TIMED_WAIT(bar, par, acc) do { if (kProbe && probe) { const long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
 
 struct TcItem {
   int b, g0, s0, ns, k, p0, p1, rows, x0, nch, pj0, pj1;   // x0: p0 rounded down to 8 tokens (TMA needs 16-byte
@@ -191,6 +193,24 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&v)[32]) {
                  "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                :
                : "memory");
+}
+// partial sum of a further accumulator chain: acc += TMEM piece (fp32 round-to-nearest adds in registers); 8 columns at a
+// time -- this is the rare long-cluster path and must not cost the common path registers
+__device__ __forceinline__ void tc_acc32(uint32_t taddr, uint32_t (&acc)[32]) {
+#pragma unroll
+  for (int j0 = 0; j0 < 32; j0 += 8) {
+    uint32_t w0, w1, w2, w3, w4, w5, w6, w7;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7)
+        : "r"(taddr + j0)
+        : "memory");
+    const uint32_t w[8] = {w0, w1, w2, w3, w4, w5, w6, w7};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      acc[j0 + j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[j0 + j]), __uint_as_float(w[j])));
+  }
 }
 __device__ __forceinline__ float tc_sumsq(const uint32_t (&v)[32], int nb) {
   float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
@@ -278,7 +298,9 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
-template <typename OutT>
+// kProbe: development build of the kernel with the per-role cycle counters (tools/agg_tc_probe.py); the product
+// instantiation carries none of them (they cost the epilogue registers)
+template <typename OutT, bool kProbe>
 __global__ void __launch_bounds__(kTcThreadsAgg, 1)
 aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_constant__ CUtensorMap map_out,
                     const int* __restrict__ tile_tbl,
@@ -339,7 +361,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
           }
         }
       }
-      if (probe) probe[blockIdx.x * 16 + 9] = t_wait;
+      if (kProbe && probe) probe[blockIdx.x * 16 + 9] = t_wait;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -351,18 +373,24 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
         if (it.rows == 0) continue;
         const int n_inst = P + (it.pj1 - it.pj0);
-        for (int inst = 0; inst < n_inst; ++inst, ++ti) {
+        for (int inst = 0; inst < n_inst; ++inst) {
           const int pass = inst < P ? inst : it.pj0 + inst - P;
           const int width = min(kTcPassN, D - pass * kTcPassN);
           // kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 @17, M>>4 @24
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) |
                                  ((uint32_t)(kTcSegTile >> 4) << 24);
-          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-          TC_TIMED_WAIT(bar_tempty + 8 * buf, (use & 1) ^ 1, t_tempty);
-          tc_fence_after();
-          TC_MARK(ti, 0);
-          const uint32_t d_tmem = tmem_base + buf * kTcPassN;
+          // one accumulator chain covers at most kTcSubChunks token chunks (header: bounded truncation); a longer cluster
+          // continues in the next TMEM buffer and the epilogue adds the partial sums
+          uint32_t buf = 0, d_tmem = 0;
           for (int c = 0; c < it.nch; ++c) {
+            const int cs = c % kTcSubChunks;
+            if (cs == 0) {
+              buf = ti % kTcBufs;
+              TC_TIMED_WAIT(bar_tempty + 8 * buf, ((ti / kTcBufs) & 1) ^ 1, t_tempty);
+              tc_fence_after();
+              if (c == 0) TC_MARK(ti, 0);
+              d_tmem = tmem_base + buf * kTcPassN;
+            }
             TC_TIMED_WAIT(bar_full + 8 * stage, phase, t_full);
             tc_fence_after();
             if (c == 0) TC_MARK(ti, 1);
@@ -375,18 +403,21 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
             for (int kk = 0; kk < nk; ++kk) {
               const uint64_t adv = (uint64_t)(kk * 2);                  // 16 tokens = 32 bytes along K
               // lo, mid, hi: small terms first
-              tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv, idesc, (c | kk) != 0);
+              tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv, idesc, (cs | kk) != 0);
               tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv + (kTcTileBytes >> 4), idesc, 1u);
               tc_mma_bf16(d_tmem, adesc + adv, bdesc + adv + 2 * (kTcTileBytes >> 4), idesc, 1u);
             }
             tc_commit(bar_empty + 8 * stage);
             if (++stage == kTcStages) { stage = 0; phase ^= 1; }
+            if (cs == kTcSubChunks - 1 || c == it.nch - 1) {   // this chain is complete
+              tc_commit(bar_tfull + 8 * buf);
+              TC_MARK(ti, 2);
+              ++ti;
+            }
           }
-          tc_commit(bar_tfull + 8 * buf);
-          TC_MARK(ti, 2);
         }
       }
-      if (probe) { probe[blockIdx.x * 16 + 6] = t_tempty; probe[blockIdx.x * 16 + 7] = t_full;
+      if (kProbe && probe) { probe[blockIdx.x * 16 + 6] = t_tempty; probe[blockIdx.x * 16 + 7] = t_full;
                    probe[blockIdx.x * 16 + 8] = clock64() - t_begin; }
     }
   } else if (warp == 6 || warp == 7) {
@@ -446,7 +477,7 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         }
       }
     }
-    if (probe && threadIdx.x == 192) { probe[blockIdx.x * 16 + 10] = t_bwait; probe[blockIdx.x * 16 + 11] = clock64() - t_bbegin; }
+    if (kProbe && probe && threadIdx.x == 192) { probe[blockIdx.x * 16 + 10] = t_bwait; probe[blockIdx.x * 16 + 11] = clock64() - t_bbegin; }
   } else {
     // ===================== epilogue warps: thread = segment row (TMEM lane) =====================
     // Two warps per TMEM lane quarter, each owning 64 of a pass's 128 channels: one warp per scheduler could not hide
@@ -479,33 +510,44 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
       }
       // ---- norm sweep: sum of squares of this warp's half of the block row (fp32 products, fp64 accumulation) ----
       double ssq = 0.0;
-      for (int pass = 0; pass < P; ++pass, ++ti) {
+      const int nsub = (it.nch + kTcSubChunks - 1) / kTcSubChunks;   // accumulator chains per pass (1 unless n_k > ~128)
+      for (int pass = 0; pass < P; ++pass) {
         const int width = min(kTcPassN, D - pass * kTcPassN);
         const int c0 = half * 64;
         const int w0 = min(32, width - c0), w1 = min(32, width - c0 - 32);     // columns in this warp's two pieces
-        const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-        TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_nwait);
-        tc_fence_after();
-        if (warp == 2 && lane == 0) TC_MARK(ti, 4);
-        const uint32_t tcol = tlane + buf * kTcPassN + c0;
         uint32_t va[32], vb[32];
-        if (w0 > 0) {                                  // (warp-uniform)
-          tc_ld32_issue(tcol, va);
-          if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
-          tc_ld_wait(va);
-          ssq += (double)tc_sumsq(va, w0);
-          if (w1 > 0) { tc_ld_wait(vb); ssq += (double)tc_sumsq(vb, w1); }
+        for (int sub = 0; sub < nsub; ++sub, ++ti) {
+          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+          TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_nwait);
+          tc_fence_after();
+          if (warp == 2 && lane == 0) TC_MARK(ti, 4);
+          const uint32_t tcol = tlane + buf * kTcPassN + c0;
+          if (w0 > 0) {                                  // (warp-uniform)
+            if (sub == 0) {
+              tc_ld32_issue(tcol, va);
+              if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
+              tc_ld_wait(va);
+              if (w1 > 0) tc_ld_wait(vb);
+            } else {
+              tc_acc32(tcol, va);
+              if (w1 > 0) tc_acc32(tcol + 32, vb);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          if (warp == 2 && lane == 0) TC_MARK(ti, 5);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        if (warp == 2 && lane == 0) TC_MARK(ti, 5);
+        if (w0 > 0) {
+          ssq += (double)tc_sumsq(va, w0);
+          if (w1 > 0) ssq += (double)tc_sumsq(vb, w1);
+        }
       }
       double* xs = s_ssq + (n_done & 1) * 2 * kTcSegTile;
       xs[half * kTcSegTile + row] = ssq;
-      { const long long _t = probe ? clock64() : 0;
+      { const long long _t = (kProbe && probe) ? clock64() : 0;
         asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
-        if (probe) t_bar += clock64() - _t; }
+        if (kProbe && probe) t_bar += clock64() - _t; }
       ssq = xs[row] + xs[kTcSegTile + row];
       ++n_done;
       const double nrm = sqrt(ssq);
@@ -515,28 +557,36 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cpred[s]), kEpsTc));
       }
       // ---- write sweep: accumulator x scale -> fp64 -> 32-byte vector stores (each lane fills whole sectors of its row) ----
-      for (int pass = it.pj0; pass < it.pj1; ++pass, ++ti) {
+      for (int pass = it.pj0; pass < it.pj1; ++pass) {
         const int width = min(kTcPassN, D - pass * kTcPassN);
         const int c0 = half * 64;
         const int w0 = min(32, width - c0), w1 = min(32, width - c0 - 32);
-        const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-        TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_wwait);
-        tc_fence_after();
-        if (warp == 2 && lane == 0) TC_MARK(ti, 4);
-        const long long t_s0 = probe ? clock64() : 0;
-        const uint32_t tcol = tlane + buf * kTcPassN + c0;
         OutT* op = orow + (size_t)pass * kTcPassN + c0;
         uint32_t va[32], vb[32];
-        if (w0 > 0) {
-          tc_ld32_issue(tcol, va);
-          if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
-          tc_ld_wait(va);
-          if (w1 > 0) tc_ld_wait(vb);
+        long long t_s0 = 0;
+        for (int sub = 0; sub < nsub; ++sub, ++ti) {
+          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+          TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_wwait);
+          tc_fence_after();
+          if (warp == 2 && lane == 0) TC_MARK(ti, 4);
+          if (kProbe && sub == 0 && probe) t_s0 = clock64();
+          const uint32_t tcol = tlane + buf * kTcPassN + c0;
+          if (w0 > 0) {
+            if (sub == 0) {
+              tc_ld32_issue(tcol, va);
+              if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
+              tc_ld_wait(va);
+              if (w1 > 0) tc_ld_wait(vb);
+            } else {
+              tc_acc32(tcol, va);
+              if (w1 > 0) tc_acc32(tcol + 32, vb);
+            }
+          }
+          // the accumulator is in registers: hand the TMEM buffer back before the (slow) stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        // the accumulator is in registers: hand the TMEM buffer back before the (slow) stores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         if (tma_rows && w0 == 32) {                      // (warp-uniform) all 32 rows valid, full 32-column pieces
           const int xcol = it.k * D + pass * kTcPassN + c0;
           const int yrow = it.s0 + quarter * 32;
@@ -566,12 +616,12 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
           TcOut<OutT>::store(op, va, sc, w0);
           if (w1 > 0) TcOut<OutT>::store(op + 32, vb, sc, w1);
         }
-        if (probe) t_store += clock64() - t_s0;
-        if (warp == 2 && lane == 0) TC_MARK(ti, 5);
+        if (kProbe && probe) t_store += clock64() - t_s0;
+        if (warp == 2 && lane == 0) TC_MARK(ti - 1, 5);
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging boxes drained before exit
-    if (probe && warp == 2 && lane == 0) {
+    if (kProbe && probe && warp == 2 && lane == 0) {
       unsigned long long* pr = probe + blockIdx.x * 16;
       pr[0] = clock64() - t_ebegin; pr[1] = t_nwait; pr[3] = t_bar; pr[4] = t_wwait; pr[5] = t_store; pr[12] = n_done;
     }
@@ -611,10 +661,11 @@ static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, in
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
   }
-  SV_CHECK_CUDA(cudaFuncSetAttribute(aggregate_tc_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = a.probe ? aggregate_tc_kernel<OutT, true> : aggregate_tc_kernel<OutT, false>;
+  SV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
-  aggregate_tc_kernel<OutT><<<grid, kTcThreadsAgg, smem, st>>>(map, map_out, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K,
-                                                             n_items, J, reinterpret_cast<OutT*>(a.out), a.norms, a.probe, store_hint);
+  kern<<<grid, kTcThreadsAgg, smem, st>>>(map, map_out, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K, n_items, J,
+                                          reinterpret_cast<OutT*>(a.out), a.norms, a.probe, store_hint);
   prof_end(pslot, st);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;

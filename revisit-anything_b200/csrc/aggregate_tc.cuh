@@ -10,6 +10,11 @@ namespace segvlad {
 constexpr int kTcSegTile = 128;   // segments per MMA tile (M)
 constexpr int kTcTokChunk = 64;   // tokens per K chunk (one 128-byte swizzle row of bf16)
 constexpr int kTcPassN = 128;     // descriptor channels per accumulator pass (N)
+// TMEM accumulation truncates: every accumulating MMA can cost the running sum up to one ulp, coherently (measured ~6e-8
+// relative per MMA).  One accumulator chain therefore covers at most kTcSubChunks token chunks (128 tokens = 24 MMAs,
+// <= 2.9e-6 relative worst case, ~1.4e-6 typical); the chains of a longer cluster land in successive TMEM buffers and the
+// epilogue adds them with fp32 round-to-nearest adds in registers (<= 12 of them for a 1530-token image).
+constexpr int kTcSubChunks = 2;
 
 struct AggTcArgs {
   const float* R;             // [B][N][D] fp32 residual rows (token-major), or null: build RT from the tokens (below)

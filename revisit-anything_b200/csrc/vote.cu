@@ -20,13 +20,16 @@ namespace segvlad {
 constexpr int kVoteThreads = 1024;
 constexpr int kVoteSmemHits = 8192;  // 24 B per hit slot -> 192 KB dynamic shared memory
 
-__global__ void minmax_kernel(const float* __restrict__ sims, long long total, int ld, int kv, int is_d2,
-                              uint32_t* __restrict__ mm) {
+// kNN padding entries (match < 0: a bank or shard with fewer than k_vote rows) are not hits and carry d2 = +inf; they
+// are left out of the global min / max (with them lo = -inf and every vote weight would be NaN)
+__global__ void minmax_kernel(const long long* __restrict__ matches, const float* __restrict__ sims, long long total, int ld,
+                              int kv, int is_d2, uint32_t* __restrict__ mm) {
   float lo = INFINITY, hi = -INFINITY;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long row = i / kv;
     int col = (int)(i - row * kv);
+    if (matches[row * ld + col] < 0) continue;
     float v = sims[row * ld + col];
     if (is_d2) v = __fsub_rn(2.0f, v);
     lo = fminf(lo, v);
@@ -57,7 +60,8 @@ __device__ __forceinline__ bool vote_better(double sa, unsigned ta, double sb, u
 
 __global__ void __launch_bounds__(kVoteThreads)
 vote_kernel(const long long* __restrict__ matches, const float* __restrict__ sims, int ld, int is_d2, int kv,
-            const int* __restrict__ qimg_off, const int* __restrict__ rimg, int Nr, int n_rimg, int n_pred,
+            const int* __restrict__ qimg_off, const int* __restrict__ qrow, const int* __restrict__ rimg, int Nr,
+            int n_rimg, int n_pred,
             const uint32_t* __restrict__ mm, int* __restrict__ preds, double* __restrict__ pred_scores,
             double* __restrict__ scores_dense, int* __restrict__ counts_dense, char* __restrict__ scratch,
             int P_cap) {
@@ -81,7 +85,7 @@ vote_kernel(const long long* __restrict__ matches, const float* __restrict__ sim
     unsigned long long key = ~0ull;
     if (t < H) {
       const int s = t % n, k = t / n;
-      const size_t off = (size_t)(q0 + s) * ld + k;
+      const size_t off = (size_t)(qrow ? qrow[q0 + s] : q0 + s) * ld + k;
       const long long m = matches[off];
       float v = sims[off];
       if (is_d2) v = __fsub_rn(2.0f, v);
@@ -191,10 +195,10 @@ extern "C" size_t segvlad_vote_workspace_bytes(int Nq, int k_vote, int n_qimg, i
 }
 
 extern "C" int segvlad_vote(const int64_t* matches, const float* sims, int ld, int sims_is_d2, int k_vote, int Nq,
-                            const int32_t* qimg_offsets, int n_qimg, int max_segs_per_qimg,
-                            const int32_t* rseg_to_rimg, int Nr, int n_rimg, int n_pred, int32_t* preds,
-                            double* pred_scores, double* scores_dense, int32_t* counts_dense, float* minmax_out,
-                            void* workspace, size_t workspace_bytes, void* stream_) {
+                            const int32_t* qimg_offsets, const int32_t* qrow_index, int n_qimg,
+                            int max_segs_per_qimg, const int32_t* rseg_to_rimg, int Nr, int n_rimg, int n_pred,
+                            int32_t* preds, double* pred_scores, double* scores_dense, int32_t* counts_dense,
+                            float* minmax_out, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   SV_REQUIRE(Nq >= 0 && k_vote > 0 && ld >= k_vote && n_qimg >= 0 && n_pred > 0 && Nr > 0 && n_rimg > 0,
              "vote: bad shape");
@@ -213,7 +217,8 @@ extern "C" int segvlad_vote(const int64_t* matches, const float* sims, int ld, i
   if (total > 0) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    minmax_kernel<<<blocks, 256, 0, st>>>(sims, total, ld, k_vote, sims_is_d2, mm);
+    minmax_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const long long*>(matches), sims, total, ld, k_vote, sims_is_d2,
+                                          mm);
     SV_CHECK_LAUNCH();
   }
   if (minmax_out) {
@@ -228,7 +233,7 @@ extern "C" int segvlad_vote(const int64_t* matches, const float* sims, int ld, i
   const size_t smem = (size_t)(Pmax > kVoteSmemHits ? kVoteSmemHits : Pmax) * 24;
   SV_CHECK_CUDA(cudaFuncSetAttribute(vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kVoteSmemHits * 24));
   vote_kernel<<<n_qimg, kVoteThreads, smem, st>>>(reinterpret_cast<const long long*>(matches), sims, ld, sims_is_d2,
-                                                 k_vote, qimg_offsets, rseg_to_rimg, Nr, n_rimg, n_pred, mm, preds,
+                                                 k_vote, qimg_offsets, qrow_index, rseg_to_rimg, Nr, n_rimg, n_pred, mm, preds,
                                                  pred_scores, scores_dense, counts_dense, scratch, P_cap);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;

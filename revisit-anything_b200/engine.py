@@ -94,7 +94,7 @@ def aggregate_batch(tokens: torch.Tensor, N: int, D: int, token_layout: int, cen
             if a is None:
                 a = torch.eye(Si, dtype=torch.uint8, device=dev)
             assert a.shape == (Si, Si), "adjacency shape mismatch"
-            parts.append(a.to(device=dev, dtype=torch.uint8).reshape(-1))
+            parts.append((a.to(dev) != 0).to(torch.uint8).reshape(-1))   # any nonzero entry counts (reference: .bool())
         adj_flat = torch.cat(parts).contiguous() if parts else None
     odt = OUT_F64 if out_dtype == torch.float64 else OUT_F32
     out = torch.empty((S_total, K * D), dtype=torch.float64 if odt == OUT_F64 else torch.float32, device=dev)
@@ -127,7 +127,7 @@ def aggregate_residuals(residuals: torch.Tensor, labels: torch.Tensor, N: int, D
         for b in range(B):
             Si = int(seg_counts[b])
             a = adj[b] if adj[b] is not None else torch.eye(Si, dtype=torch.uint8, device=dev)
-            parts.append(a.to(device=dev, dtype=torch.uint8).reshape(-1))
+            parts.append((a.to(dev) != 0).to(torch.uint8).reshape(-1))
         adj_flat = torch.cat(parts).contiguous()
     odt = OUT_F64 if out_dtype == torch.float64 else OUT_F32
     out = torch.empty((S_total, K * D), dtype=torch.float64 if odt == OUT_F64 else torch.float32, device=dev)
@@ -257,9 +257,11 @@ class VoteResult:
 
 def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, rseg_to_rimg: torch.Tensor,
          n_rimg: int, n_pred: int = 5, k_vote: int = 50, sims_is_d2: bool = False, dense: bool = False,
-         max_segs: Optional[int] = None) -> VoteResult:
+         max_segs: Optional[int] = None, qrow_index: Optional[torch.Tensor] = None) -> VoteResult:
     """Similarity-weighted segment->image vote (get_matches 'max_seg_topk_wt_borda_Im' semantics) + hit
-    counts.  matches/sims: [Nq, ld] int64 / fp32 (first k_vote columns used); qimg_offsets [n_qimg+1] int32."""
+    counts.  matches/sims: [Nq, ld] int64 / fp32 (first k_vote columns used); qimg_offsets [n_qimg+1] int32;
+    qrow_index (optional int32): rows of matches/sims in concatenated segRangeQuery order (None: identity).  The
+    min/max normalisation always spans all Nq rows (func_vpr.py:211-212)."""
     _need_cuda(matches, sims, qimg_offsets, rseg_to_rimg)
     assert matches.dtype == torch.int64 and sims.dtype == torch.float32
     assert matches.stride(1) == 1 and sims.stride(1) == 1 and matches.stride(0) == sims.stride(0)
@@ -269,6 +271,8 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
     qimg_offsets = qimg_offsets.to(device=dev, dtype=torch.int32).contiguous()
     rseg_to_rimg = rseg_to_rimg.to(device=dev, dtype=torch.int32).contiguous()
     n_qimg = qimg_offsets.numel() - 1
+    if qrow_index is not None:
+        qrow_index = qrow_index.to(device=dev, dtype=torch.int32).contiguous()
     if max_segs is None:
         max_segs = int((qimg_offsets[1:] - qimg_offsets[:-1]).max().item()) if n_qimg > 0 else 0
     preds = torch.empty((n_qimg, n_pred), dtype=torch.int32, device=dev)
@@ -277,8 +281,8 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
     counts = torch.empty((n_qimg, n_rimg), dtype=torch.int32, device=dev) if dense else None
     mm = torch.empty(2, dtype=torch.float32, device=dev)
     ws = _ws(lib().segvlad_vote_workspace_bytes(Nq, k_vote, n_qimg, max_segs), dev)
-    check(lib().segvlad_vote(_ptr(matches), _ptr(sims), ld, int(sims_is_d2), k_vote, Nq, _ptr(qimg_offsets), n_qimg,
-                             max_segs, _ptr(rseg_to_rimg), rseg_to_rimg.numel(), n_rimg, n_pred, _ptr(preds),
+    check(lib().segvlad_vote(_ptr(matches), _ptr(sims), ld, int(sims_is_d2), k_vote, Nq, _ptr(qimg_offsets),
+                             _ptr(qrow_index), n_qimg, max_segs, _ptr(rseg_to_rimg), rseg_to_rimg.numel(), n_rimg, n_pred, _ptr(preds),
                              _ptr(pscores), _ptr(scores), _ptr(counts), _ptr(mm), _ptr(ws), ws.numel(), _stream()),
           "segvlad_vote")
     return VoteResult(preds, pscores, scores, counts, mm)

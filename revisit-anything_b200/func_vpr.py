@@ -215,45 +215,68 @@ def _ranges_to_offsets(segRangeQuery, n_img):
     return (None if contiguous else cat), off
 
 
+def _get_matches_host(matches, gt, sims, segRangeQuery, imIndsRef, n, method):
+    """The two analysis variants that work on ONE match per query segment (matches / sims are 1-D [Nq], the top-1 column):
+    "max_sim" (func_vpr.py:87-93, the signature's default) and "max_seg_sim" (:103-117).  A few numpy calls per query
+    image on [n_seg] arrays -- host glue like calc_recall, kept on the host exactly as the reference has it."""
+    matches, sims, imIndsRef = np.asarray(matches), np.asarray(sims), np.asarray(imIndsRef)
+    preds = []
+    for i in range(len(gt)):
+        rows = segRangeQuery[i]
+        if method == "max_sim":
+            order = np.flip(np.argsort(sims[rows])[-50:])
+            preds.append(first_k_unique_indices(imIndsRef[matches[rows][order]], n))
+            continue
+        hit_img = imIndsRef[matches[rows]]
+        cnt = np.bincount(hit_img)
+        ids = np.where(cnt > 0)[0]
+        cand = ids[np.flip(np.argsort(cnt[ids])[-6:])]
+        best = [np.max(sims[rows][np.where(hit_img == c)[0]]) for c in cand]
+        preds.append(cand[np.flip(np.argsort(best))][:n])
+    return preds
+
+
 def get_matches(matches, gt, sims, segRangeQuery, imIndsRef, n=1, method="max_sim"):
-    """func_vpr.py:80-243 for the methods the drivers use: "max_seg_topk_wt_borda_Im" (default of
-    recall_segloc), "max_seg_topk" and "max_seg".  Returns a list (per query image) of arrays of
-    reference-image ids, best first.  Methods whose reference branch calls undefined helpers raise."""
+    """func_vpr.py:80-243.  "max_seg_topk_wt_borda_Im" (the method recall_segloc uses, place_rec_main.py:84),
+    "max_seg_topk" and "max_seg" run in the vote kernel; "max_sim" (the default argument) and "max_seg_sim" are the
+    reference's per-image numpy one-liners on top-1 matches and stay on the host.  Returns a list (per query image) of
+    reference-image ids, best first.  Methods whose reference branch calls undefined helpers (merge_ranked_lists,
+    average_rank_method, ...) raise."""
+    if method in ("max_sim", "max_seg_sim"):
+        return _get_matches_host(matches, gt, sims, segRangeQuery, imIndsRef, n, method)
+    if method not in ("max_seg_topk_wt_borda_Im", "max_seg_topk", "max_seg"):
+        raise NotImplementedError(f"get_matches: method {method!r} is not on the SegVLAD hot path "
+                                  "(its reference branch is dead code: it calls helpers the reference never defines)")
     dev = _dev()
     n_img = len(gt)
     perm, off = _ranges_to_offsets(segRangeQuery, n_img)
     m = torch.as_tensor(np.asarray(matches))
     if method == "max_seg":
         m = m.reshape(-1, 1)
-    m = m.to(dev).to(torch.int64)
+    m = m.to(dev).to(torch.int64).contiguous()
     if method in ("max_seg_topk", "max_seg"):
         s = torch.zeros(m.shape, dtype=torch.float32, device=dev)
     else:
-        s = torch.as_tensor(np.asarray(sims), dtype=torch.float32).to(dev)
-    if perm is not None:
-        pidx = torch.from_numpy(perm).to(dev)
-        m, s = m[pidx].contiguous(), s[pidx].contiguous()
-    else:
-        m, s = m.contiguous(), s.contiguous()
+        s = torch.as_tensor(np.asarray(sims), dtype=torch.float32).to(dev).contiguous()
+    # non-contiguous / partial segRangeQuery: the kernel reads rows through an index list, the min / max normalisation
+    # still spans the WHOLE sims array like np.min(sims) / np.max(sims) at func_vpr.py:211-212
+    qrow = None if perm is None else torch.from_numpy(perm.astype(np.int32)).to(dev)
     im = np.asarray(imIndsRef).astype(np.int64)
     n_rimg = int(im.max()) + 1 if im.size else 1
     rimg = torch.from_numpy(im).to(dev)
     offs = torch.from_numpy(off.astype(np.int32)).to(dev)
     if method == "max_seg_topk_wt_borda_Im":
-        res = engine.vote(m, s, offs, rimg, n_rimg, n_pred=n, k_vote=m.shape[1])
+        res = engine.vote(m, s, offs, rimg, n_rimg, n_pred=n, k_vote=m.shape[1], qrow_index=qrow)
         p = res.preds.cpu().numpy()
         return [p[i][p[i] >= 0].astype(np.int64) for i in range(n_img)]
-    if method in ("max_seg_topk", "max_seg"):
-        res = engine.vote(m, s, offs, rimg, n_rimg, n_pred=1, k_vote=m.shape[1], dense=True)
-        c = res.counts.cpu().numpy()
-        out = []
-        for i in range(n_img):
-            ids = np.where(c[i] > 0)[0]
-            order = np.argsort(c[i][ids], kind="stable")   # (count desc, larger id first), see DESIGN.md
-            out.append(ids[np.flip(order[-n:])])
-        return out
-    raise NotImplementedError(f"get_matches: method {method!r} is not on the SegVLAD hot path "
-                              "(its reference branch is dead code or an analysis variant)")
+    res = engine.vote(m, s, offs, rimg, n_rimg, n_pred=1, k_vote=m.shape[1], dense=True, qrow_index=qrow)
+    c = res.counts.cpu().numpy()
+    out = []
+    for i in range(n_img):
+        ids = np.where(c[i] > 0)[0]
+        order = np.argsort(c[i][ids], kind="stable")   # (count desc, larger id first), see DESIGN.md
+        out.append(ids[np.flip(order[-n:])])
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

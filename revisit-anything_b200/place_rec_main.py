@@ -44,14 +44,11 @@ def search_and_vote(seg_ft_ref: torch.Tensor, seg_ft_qry: torch.Tensor, seg_rang
         qbank = prep(seg_ft_qry)
         d2, idx = engine.knn(qbank, rbank, k_search)
     perm, off = func_vpr._ranges_to_offsets(seg_range_q, n_qimg)
-    m, s = idx, d2
-    if perm is not None:
-        pidx = torch.from_numpy(perm).to(dev)
-        m, s = idx[pidx].contiguous(), d2[pidx].contiguous()
+    qrow = None if perm is None else torch.from_numpy(perm.astype(np.int32)).to(dev)
     im = np.asarray(im_inds_ref).astype(np.int64)
     n_rimg = int(im.max()) + 1
-    res = engine.vote(m, s, torch.from_numpy(off.astype(np.int32)).to(dev), torch.from_numpy(im).to(dev), n_rimg,
-                      n_pred=n_pred, k_vote=k_vote, sims_is_d2=True)
+    res = engine.vote(idx, d2, torch.from_numpy(off.astype(np.int32)).to(dev), torch.from_numpy(im).to(dev), n_rimg,
+                      n_pred=n_pred, k_vote=k_vote, sims_is_d2=True, qrow_index=qrow)
     return d2, idx, res
 
 

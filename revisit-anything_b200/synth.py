@@ -44,6 +44,23 @@ def make_tokens(D: int, dh: int, dw: int, seed: int, centers: torch.Tensor | Non
     return x.reshape(1, D, dh, dw).contiguous()
 
 
+def make_tokens_skewed(D: int, dh: int, dw: int, seed: int, centers: torch.Tensor, frac: float,
+                       heavy: int = 0) -> torch.Tensor:
+    """[1,D,dh,dw] fp32 unit-norm tokens of a sky / road dominated image: a fraction `frac` of the tokens is pulled
+    towards ONE centre (`heavy`), the rest towards random centres -> one cluster holds ~frac of the image."""
+    g = torch.Generator().manual_seed(2500 + seed)
+    N = dh * dw
+    K = centers.shape[0]
+    x = torch.randn(D, N, generator=g)
+    x = x / x.norm(dim=0, keepdim=True)
+    pick = torch.randint(0, K, (N,), generator=g)
+    pick[torch.rand(N, generator=g) < frac] = heavy
+    cn = centers / centers.norm(dim=1, keepdim=True)
+    x = x + 0.6 * cn[pick].T
+    x = x / x.norm(dim=0, keepdim=True).clamp_min(1e-12)
+    return x.reshape(1, D, dh, dw).contiguous()
+
+
 def make_masks(S: int, Hm: int, Wm: int, seed: int) -> list:
     """S non-empty bool masks [Hm,Wm]: union of 1-3 axis-aligned rectangles, area fraction
     log-uniform in [2e-3, 0.2]."""

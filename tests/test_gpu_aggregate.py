@@ -80,6 +80,87 @@ def test_variants_vs_oracle(D, K, order, S):
     _check_against_oracle(seed=7 + D + K, D=D, H=196, W=266, S=S, K=K, order=order)
 
 
+def test_north_star_table_k64_d1536_vs_oracle():
+    # BASELINE north_star: 64 x 1536 centroid table at the 640x480 token grid
+    _check_against_oracle(seed=164, D=1536, H=480, W=640, S=24, K=64, order=3)
+
+
+def test_config5_table_k128_d768_vs_oracle():
+    _check_against_oracle(seed=1128, D=768, H=322, W=322, S=19, K=128, order=2)
+
+
+def test_canonical_150_segments_multi_tile_vs_oracle():
+    # S = 150 (the survey's canonical image): two segment tiles (128 + 22), the 32-row store boxes end inside the image
+    _check_against_oracle(seed=150, D=512, H=480, W=640, S=150, K=32, order=3)
+
+
+def test_batch_of_tiles_at_image_boundaries_vs_oracle():
+    # [150, 129, 128, 1]: tile tails of 22 / 1 / 0 rows and a single-segment image share one launch; a bulk store box
+    # must never cross into the next image's rows
+    dev = torch.device("cuda")
+    D, H, W, K = 128, 224, 308, 32
+    N = (H // 14) * (W // 14)
+    cfg = {"desired_height": H, "desired_width": W}
+    centers = synth.make_centers(K, D, 8)
+    toks, bits, counts, adjs, wants = [], [], [], [], []
+    for i, S in enumerate([150, 129, 128, 1]):
+        tokens = synth.make_tokens(D, H // 14, W // 14, 400 + i, centers)
+        masks = synth.make_masks(S, H // 2, W // 2, 500 + i)
+        adj = torch.from_numpy(O.neighbour_adjacency(masks, 2))
+        want, _, margin, _ = O.seg_vlad_single_img(tokens, masks, centers, cfg, adj)
+        assert float(margin.min()) > 1e-5
+        toks.append(tokens.reshape(D, N)); counts.append(S); adjs.append(adj); wants.append(want.numpy())
+        bits.append(engine.mask_to_membership(torch.from_numpy(np.asarray(masks)).to(dev), H, W))
+    for dt in (torch.float64, torch.float32):
+        got = engine.aggregate_batch(torch.stack(toks).to(dev), N, D, TOKENS_DN, centers.to(dev), torch.cat(bits), counts,
+                                     adjs, out_dtype=dt).cpu().numpy()
+        _cmp(got, np.concatenate(wants))
+
+
+@pytest.mark.parametrize("frac", [0.6, 0.95])
+@pytest.mark.parametrize("D,K", [(1536, 32), (256, 64)])
+def test_skewed_vocabulary_one_dominant_cluster(frac, D, K):
+    # one cluster holds 60 % / 95 % of the image's 1530 tokens (~900 / ~1450 tokens): the accumulator chain of such a
+    # cluster is split into bounded sub-chains (csrc/aggregate_tc.cuh kTcSubChunks), the error must not grow with n_k
+    dev = torch.device("cuda")
+    H, W, S = 480, 640, 12
+    N = (H // 14) * (W // 14)
+    cfg = {"desired_height": H, "desired_width": W}
+    centers = synth.make_centers(K, D, 77)
+    tokens = synth.make_tokens_skewed(D, H // 14, W // 14, 31 + K, centers, frac, heavy=3)
+    masks = synth.make_masks(S, H // 2, W // 2, 33)
+    adj = torch.from_numpy(O.neighbour_adjacency(masks, 3))
+    want, labels, margin, _ = O.seg_vlad_single_img(tokens, masks, centers, cfg, adj)
+    assert int((labels == 3).sum()) > 0.9 * frac * N
+    safe = margin.numpy() > 1e-5
+    assert safe.all()
+    bits = engine.mask_to_membership(torch.from_numpy(np.asarray(masks)).to(dev), H, W)
+    got, lab = engine.aggregate_batch(tokens.reshape(D, N).to(dev), N, D, TOKENS_DN, centers.to(dev), bits, [S], [adj],
+                                      return_labels=True)
+    np.testing.assert_array_equal(lab.cpu().numpy()[0], labels.numpy())
+    _cmp(got.cpu().numpy(), want.numpy())
+    # the AnyLoc whole-image path feeds ALL tokens of the image to one segment (utilities.VLAD, S = 1)
+    from revisit_anything_b200.utilities import VLAD
+    v = VLAD(K, desc_dim=None, dist_mode="cosine", vlad_mode="hard", cache_dir=None)
+    v.set_centers(centers)
+    tok_nd = tokens.reshape(D, N).t().contiguous()
+    _cmp(v.generate(tok_nd).numpy()[None], O.anyloc_vlad_generate(tok_nd, centers).numpy()[None])
+
+
+def test_seg_vlad_gpu_single_with_mapping():
+    # the function north_star names (func_vpr.py:1065-1101): tokens come out of an h5py-like mapping
+    H, W, D, K, S = 196, 266, 96, 32, 7
+    cfg = {"desired_height": H, "desired_width": W}
+    centers, tokens, masks, adj = _image(5, D, H, W, S, K, 2)
+    store = {"img_000.jpg": {"ift_dino": tokens.numpy()}}
+    gd = func_vpr.seg_vlad_gpu_single(None, None, store, "img_000.jpg", masks, centers, cfg, desc_dim=D, adj_mat=adj)
+    assert gd.dtype == torch.float64 and not gd.is_cuda and tuple(gd.shape) == (S, K * D)
+    want = O.seg_vlad_single_img(tokens, masks, centers, cfg, adj)[0]
+    _cmp(gd.numpy(), want.numpy())
+    twin = func_vpr.seg_vlad_gpu_single_img(None, None, tokens, "img_000.jpg", masks, centers, cfg, desc_dim=D, adj_mat=adj)
+    np.testing.assert_array_equal(gd.numpy(), twin.numpy())
+
+
 def test_token_major_layout_and_f32_output():
     _check_against_oracle(seed=55, D=384, H=196, W=266, S=12, K=32, order=2, layout=TOKENS_ND)
     _check_against_oracle(seed=56, D=384, H=196, W=266, S=12, K=32, order=2, out_dtype=torch.float32)

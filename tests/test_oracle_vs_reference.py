@@ -92,3 +92,29 @@ def test_adjacency_vs_reference(ref, S, order, seed):
     """a4: SuperSegment adjacency (Delaunay neighbours to the given order, func_vpr.py:1309-1347) incl. the S <= 3 special case."""
     masks = synth.make_masks(S, 48, 64, seed)
     np.testing.assert_array_equal(O.neighbour_adjacency(masks, order), ref.nbrMasksAGGFastSingle(masks, order).numpy())
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("method", ["max_sim", "max_seg_sim"])
+def test_host_get_matches_variants_vs_reference(ref, seed, method):
+    """a7 boundary: the signature's DEFAULT method "max_sim" (func_vpr.py:87-93) and "max_seg_sim" (:103-117) work on the
+    top-1 match per query segment; the drop-in keeps them on the host.  Compared with the unmodified reference, including
+    a non-contiguous segRangeQuery."""
+    from revisit_anything_b200 import func_vpr as ours
+    rng = np.random.RandomState(seed)
+    n_qimg, Nr = 9, 400
+    lens = rng.randint(3, 70, size=n_qimg)
+    Nq = int(lens.sum())
+    perm = rng.permutation(Nq) if seed else np.arange(Nq)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    seg_range = [perm[off[i]:off[i + 1]] for i in range(n_qimg)]
+    im_inds_ref = np.sort(rng.randint(0, 30, size=Nr)).astype(np.int64)
+    matches = rng.randint(0, Nr, size=Nq).astype(np.int64)
+    sims = rng.permutation(Nq).astype(np.float32) / Nq          # distinct values: argsort order is unique
+    gt = [[0]] * n_qimg
+    want = ref.get_matches(matches, gt, sims, seg_range, im_inds_ref, n=5, method=method)
+    got = ours.get_matches(matches, gt, sims, seg_range, im_inds_ref, n=5, method=method)
+    assert [list(map(int, p)) for p in got] == [list(map(int, p)) for p in want]
+    if method == "max_sim":                                     # the default argument must be this branch
+        dflt = ours.get_matches(matches, gt, sims, seg_range, im_inds_ref, n=5)
+        assert [list(map(int, p)) for p in dflt] == [list(map(int, p)) for p in want]
