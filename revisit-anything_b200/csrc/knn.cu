@@ -574,8 +574,34 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 //                   (d2 bits << 32 | idx) => ascending (d2, idx); the first k are written out (global row = offset + idx).
 //   kRefineExactK : exact values, conservative schedule.  Same sort, the first k go back to the candidate list
 //                   (count = k exactly, ties broken by index like the final order), tau = T.
-enum { kRefineSelect = 0, kRefineFinal = 1, kRefineExactK = 2 };
+//   kRefineSelectLoose : kRefineSelect for the rounds BETWEEN scan chunks, where T only has to be an upper bound of the
+//                   k-th best: the digit loop stops as soon as the bin holding the k-th value has <= kLooseBin
+//                   members and T = that bin's largest possible value (one histogram pass instead of three or four
+//                   for ~10 % more survivors; the pass before the exact re-score stays tight).
+enum { kRefineSelect = 0, kRefineFinal = 1, kRefineExactK = 2, kRefineSelectLoose = 3 };
+constexpr int kLooseBin = 32;
 constexpr int kSmallSort = 512;   // up to this many candidates: sort them all, no selection passes
+
+// n <= 512 unique keys: every thread ranks its own keys against all others (broadcast shared-memory reads, no barriers
+// inside) and drops them at their rank -- for the ~k + margin candidates of a final pass this is about half the time of
+// the bitonic network with its log^2 barrier stages.  dst[n .. P) is padded with ~0.
+__device__ __forceinline__ void rank_sort_keys(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst,
+                                               int n, int P, int tid) {
+  for (int i = tid; i < P; i += 256) {
+    if (i >= n) { dst[i] = ~0ull; continue; }
+    const unsigned long long mine = src[i];
+    int rank = 0;
+    // keys are unique (a reference row is a candidate of a query at most once); equal keys would still be ordered by
+    // position, so the result is a permutation in any case
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const unsigned long long o = src[j];
+      rank += (o < mine) | ((o == mine) & (j < i));
+    }
+    dst[rank] = mine;
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ void bitonic_sort_keys(unsigned long long* keys, int P, int tid) {
   for (int kk2 = 2; kk2 <= P; kk2 <<= 1) {
@@ -602,10 +628,12 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
   __shared__ int s_hist[256];
   __shared__ int s_warp[8];
   __shared__ unsigned s_or[8], s_and[8];
-  __shared__ int s_bin, s_kk, s_out;
+  __shared__ int s_bin, s_kk, s_out, s_val;
   static_assert(sizeof(unsigned) * kCandCap * 2 == sizeof(unsigned long long) * kCandCap, "key aliasing");
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(s_v);   // s_v and s_i are contiguous: 32 KB
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool loose = mode == kRefineSelectLoose;
+  if (loose) mode = kRefineSelect;
   int n = sel.cnt[row];
   if (n > kCandCap) n = kCandCap;
   float* cd = sel.cand_d2 + (size_t)row * kCandCap;
@@ -628,7 +656,8 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
       keys[i] = i < n ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | ((unsigned)(dense_first ? i : ci[i]) & idmask))
                       : ~0ull;
     __syncthreads();
-    bitonic_sort_keys(keys, P, tid);
+    rank_sort_keys(keys, keys + kCandCap / 2, n, P, tid);
+    keys += kCandCap / 2;
     if (n > k) T = (unsigned)(keys[k - 1] >> 32);
     if (mode == kRefineSelect) {   // n > k here; the survivors are a prefix of the sorted list
       const unsigned keepT = __float_as_uint(__fadd_ru(__uint_as_float(T), twoE));
@@ -685,12 +714,16 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
       int base = 0;
       for (int ww = 0; ww < w; ++ww) base += s_warp[ww];
       const int excl = base + incl - val;
-      if (kk > excl && kk <= excl + val) { s_bin = tid; s_kk = kk - excl; }
+      if (kk > excl && kk <= excl + val) { s_bin = tid; s_kk = kk - excl; s_val = val; }
       __syncthreads();
       prefix |= (unsigned)s_bin << lo;
       mask |= dm << lo;
       kk = s_kk;
       hi = lo;
+      if (loose && compact && s_val <= kLooseBin) {   // upper bound of the k-th value: the largest value of its bin
+        prefix |= (1u << lo) - 1u;
+        break;
+      }
     }
     if (compact) T = prefix;
     // approximate scores: everything within 2E of the k-th best may still belong to the exact top k
@@ -735,7 +768,12 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
       if (i < P) keys[i] = mykeys[t];
     }
     __syncthreads();
-    bitonic_sort_keys(keys, P, tid);
+    if (c <= kSmallSort) {
+      rank_sort_keys(keys, keys + kCandCap / 2, c, P, tid);
+      keys += kCandCap / 2;
+    } else {
+      bitonic_sort_keys(keys, P, tid);
+    }
   }
   if (mode == kRefineExactK) {
     const int keep = c < k ? c : k;
@@ -794,6 +832,188 @@ knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __r
     }
     acc = warp_sum(acc);
     if (lane == 0) { cd[j] = make_d2(qnr, rn[col], acc); ci[j] = col | kExactFlag; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Re-score BY REFERENCE ROW (the final pass of a resident search).  knn_rescore_kernel above gathers ~k + margin fp32
+// reference rows per QUERY: every reference row is fetched ~Nq (k + margin) / Nr times (22 x for config 2) and the
+// kernel is bound by DRAM (r1 ncu: 10.8 GB read for a 0.61 GB bank).  Here the candidate lists are inverted first --
+// count pairs per reference row, exclusive scan, scatter (query row, slot) -- and one warp per reference row stages that
+// row in shared memory ONCE (the bank streams from HBM exactly once) and takes the query rows of its pairs from L2, which
+// holds the whole query block (16384 x D fp32 <= 100 MB).  The per-lane summation order is the one of
+// knn_rescore_kernel, so both kernels produce bit-identical values.
+struct InvState {
+  int* ref_off;     // [Nr + 1] pairs per reference row -> exclusive offsets -> (after the scatter) end offsets
+  int* blk_sum;     // [ceil(Nr / kScanTile) + 1]
+  unsigned* pairs;  // [cap] (query row << 12) | candidate slot
+  int* state;       // [0] total pairs, [1] 1: the inverted lists were built (they fit), 0: fall back to the gather kernel
+  int cap;
+};
+constexpr int kScanTile = 4096;       // elements per CTA of the offset scan (1024 threads x 4)
+constexpr int kPairsPerRow = 512;     // pair-list capacity per query row of a block (k + margin <= this, else gather kernel)
+constexpr int kRefWarps = 8;          // warps (= reference rows in flight) per CTA of knn_rescore_ref_kernel
+constexpr int kRefMaxD = 3072;        // 8 rows x 3072 x 4 B = 96 KB of shared memory per CTA
+
+__global__ void __launch_bounds__(256)
+inv_count_kernel(SelState sel, InvState inv) {
+  const int row = blockIdx.x;
+  int n = sel.cnt[row];
+  if (n > kCandCap) n = kCandCap;
+  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  int mine = 0;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const int col = ci[j];
+    if (col >= 0) { atomicAdd(inv.ref_off + col, 1); ++mine; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(inv.state, mine);
+}
+
+// exclusive scan of ref_off[0 .. n): per-tile scan + tile sums, scan of the tile sums (one CTA), add-back
+__global__ void __launch_bounds__(1024)
+inv_scan_tiles_kernel(InvState inv, int n) {
+  __shared__ int s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int base = blockIdx.x * kScanTile + tid * 4;
+  int v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = base + i < n ? inv.ref_off[base + i] : 0;
+  const int tsum = v[0] + v[1] + v[2] + v[3];
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_w[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    int x = s_w[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+    s_w[lane] = x;
+  }
+  __syncthreads();
+  int run = incl - tsum + (w ? s_w[w - 1] : 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (base + i < n) inv.ref_off[base + i] = run;
+    run += v[i];
+  }
+  if (tid == 1023) inv.blk_sum[blockIdx.x] = run;
+}
+__global__ void __launch_bounds__(1024)
+inv_scan_sums_kernel(InvState inv, int n_tiles) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < n_tiles; b0 += 1024) {
+    const int i = b0 + tid;
+    const int v = i < n_tiles ? inv.blk_sum[i] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int x = s_w[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += t; }
+      s_w[lane] = x;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    if (i < n_tiles) inv.blk_sum[i] = carry + incl - v + (w ? s_w[w - 1] : 0);
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_w[31];
+    __syncthreads();
+  }
+  if (tid == 0) inv.state[1] = (inv.state[0] > 0 && inv.state[0] <= inv.cap) ? 1 : 0;
+}
+__global__ void __launch_bounds__(1024)
+inv_scan_add_kernel(InvState inv, int n) {
+  const int add = inv.blk_sum[blockIdx.x];
+  const int base = blockIdx.x * kScanTile + threadIdx.x * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (base + i < n) inv.ref_off[base + i] += add;
+}
+
+__global__ void __launch_bounds__(256)
+inv_scatter_kernel(SelState sel, InvState inv) {
+  if (inv.state[1] == 0) return;
+  const int row = blockIdx.x;
+  int n = sel.cnt[row];
+  if (n > kCandCap) n = kCandCap;
+  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  for (int j = threadIdx.x; j < n; j += 256) {
+    const int col = ci[j];
+    if (col >= 0) inv.pairs[atomicAdd(inv.ref_off + col, 1)] = ((unsigned)row << 12) | (unsigned)j;
+  }
+}
+
+// grid-stride over reference rows, one warp per row; after the scatter ref_off[r] is the END of row r's pair list and
+// ref_off[r - 1] its start.  Shared memory: kRefWarps rows of D floats.
+__global__ void __launch_bounds__(kRefWarps * 32)
+knn_rescore_ref_kernel(SelState sel, InvState inv, const float* __restrict__ q32, const float* __restrict__ r32,
+                       const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int Nr, int D) {
+  extern __shared__ __align__(16) float s_ref[];
+  if (inv.state[1] == 0) return;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  float* my = s_ref + (size_t)w * D;
+  const bool vec = (D & 3) == 0;
+  const int nwarps = gridDim.x * kRefWarps;
+  for (int r = blockIdx.x * kRefWarps + w; r < Nr; r += nwarps) {
+    const int beg = r ? inv.ref_off[r - 1] : 0, end = inv.ref_off[r];
+    if (beg == end) continue;
+    const float* rr = r32 + (size_t)r * D;
+    __syncwarp();
+    if (vec) {
+      for (int d = lane; d < (D >> 2); d += 32)
+        reinterpret_cast<float4*>(my)[d] = __ldcs(reinterpret_cast<const float4*>(rr) + d);   // streamed once
+    } else {
+      for (int d = lane; d < D; d += 32) my[d] = __ldcs(rr + d);
+    }
+    __syncwarp();
+    const float rnr = rn[r];
+    for (int p = beg; p < end; p += 2) {
+      const bool two = p + 1 < end;
+      const unsigned pa = inv.pairs[p], pb = inv.pairs[two ? p + 1 : p];
+      const int rowa = (int)(pa >> 12), rowb = (int)(pb >> 12);
+      const float* qa = q32 + (size_t)(q_row0 + rowa) * D;
+      const float* qb = q32 + (size_t)(q_row0 + rowb) * D;
+      float acca = 0.f, accb = 0.f;
+      if (vec) {
+        const float4* a4 = reinterpret_cast<const float4*>(qa);
+        const float4* b4 = reinterpret_cast<const float4*>(qb);
+        const float4* m4 = reinterpret_cast<const float4*>(my);
+#pragma unroll 4
+        for (int d = lane; d < (D >> 2); d += 32) {
+          const float4 a = __ldg(a4 + d), b = __ldg(b4 + d), m = m4[d];
+          acca = fmaf(a.x, m.x, acca); acca = fmaf(a.y, m.y, acca); acca = fmaf(a.z, m.z, acca); acca = fmaf(a.w, m.w, acca);
+          accb = fmaf(b.x, m.x, accb); accb = fmaf(b.y, m.y, accb); accb = fmaf(b.z, m.z, accb); accb = fmaf(b.w, m.w, accb);
+        }
+      } else {
+        for (int d = lane; d < D; d += 32) {
+          const float m = my[d];
+          acca = fmaf(__ldg(qa + d), m, acca);
+          accb = fmaf(__ldg(qb + d), m, accb);
+        }
+      }
+      acca = warp_sum(acca);
+      accb = warp_sum(accb);
+      if (lane == 0) {
+        const size_t oa = (size_t)rowa * kCandCap + (pa & 4095u);
+        sel.cand_d2[oa] = make_d2(qn[q_row0 + rowa], rnr, acca);
+        sel.cand_idx[oa] = r | kExactFlag;
+        if (two) {
+          const size_t ob = (size_t)rowb * kCandCap + (pb & 4095u);
+          sel.cand_d2[ob] = make_d2(qn[q_row0 + rowb], rnr, accb);
+          sel.cand_idx[ob] = r | kExactFlag;
+        }
+      }
+    }
   }
 }
 
@@ -857,6 +1077,7 @@ __global__ void knn_debug_copy_kernel(SelState sel, ErrModel em, int q_row0, int
 // host side
 struct KnnLayout {
   SelState sel[2];   // two query blocks can be in flight (one per internal stream)
+  InvState inv[2];   // inverted candidate lists of the final re-score (one per block in flight)
   float* qn; float* rn; int* flags; int block_rows; int n_blocks; size_t total;
 };
 static KnnLayout carve_knn(void* ws, int Nq, int Nr) {
@@ -880,6 +1101,11 @@ static KnnLayout carve_knn(void* ws, int Nq, int Nr) {
     L.sel[i].cand_d2 = c.take<float>((size_t)rows * kCandCap);
     L.sel[i].cand_idx = c.take<int>((size_t)rows * kCandCap);
     L.sel[i].overflow = c.take<int>(1);
+    L.inv[i].ref_off = c.take<int>(rows ? (size_t)Nr + 1 : 0);
+    L.inv[i].blk_sum = c.take<int>(rows ? (size_t)(Nr + kScanTile - 1) / kScanTile + 1 : 0);
+    L.inv[i].cap = rows * kPairsPerRow;
+    L.inv[i].pairs = c.take<unsigned>((size_t)L.inv[i].cap);
+    L.inv[i].state = c.take<int>(4);
   }
   L.qn = c.take<float>(Nq);   // SIMT path only
   L.rn = c.take<float>(Nr);   // SIMT path only
@@ -938,7 +1164,17 @@ struct HostFeed {
 };
 struct SubChunk { int c0, c1; int first_round; int last_of_round; int final_pass; };
 
-struct BlockCtx { SelState sel; const float* qn; const float* rn; };
+struct BlockCtx { SelState sel; InvState inv; const float* qn; const float* rn; };
+
+// 0: always the per-query gather kernel; 1 (default): inverted lists for the final pass of a resident search
+static int loose_select() {
+  const char* e = getenv("SEGVLAD_KNN_LOOSE");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+static int rescore_by_ref() {
+  const char* e = getenv("SEGVLAD_KNN_RESCORE_REF");   // (read per call: the tests flip it to compare both kernels)
+  return (e && e[0] == '0') ? 0 : 1;
+}
 static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockCtx& L, int q_row0, int rows, int Nr,
                      int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
                      cudaStream_t st, const HostFeed* feed = nullptr) {
@@ -1022,6 +1258,34 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, dense, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
       const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
+      // final pass of a resident search: every row has ~k + margin candidates to re-score -> by reference row (the bank
+      // streams from HBM once); sub-chunk passes (host-streamed / conservative schedule) re-score few NEW survivors ->
+      // gather kernel.  The gather kernel also runs after the inverted pass: it skips what is exact already, i.e. it
+      // is a no-op unless the pair lists did not fit (state[1] == 0, decided on the device).
+      if (final_pass && !incremental && !safe && rescore_by_ref() && D <= kRefMaxD && Nr >= 4 * kScanTile) {
+        const int n_tiles = (Nr + kScanTile - 1) / kScanTile;
+        SV_CHECK_CUDA(cudaMemsetAsync(L.inv.ref_off, 0, sizeof(int) * ((size_t)Nr + 1), st));
+        SV_CHECK_CUDA(cudaMemsetAsync(L.inv.state, 0, sizeof(int) * 4, st));
+        inv_count_kernel<<<rows, 256, 0, st>>>(L.sel, L.inv);
+        SV_CHECK_LAUNCH();
+        inv_scan_tiles_kernel<<<n_tiles, 1024, 0, st>>>(L.inv, Nr);
+        SV_CHECK_LAUNCH();
+        inv_scan_sums_kernel<<<1, 1024, 0, st>>>(L.inv, n_tiles);
+        SV_CHECK_LAUNCH();
+        inv_scan_add_kernel<<<n_tiles, 1024, 0, st>>>(L.inv, Nr);
+        SV_CHECK_LAUNCH();
+        inv_scatter_kernel<<<rows, 256, 0, st>>>(L.sel, L.inv);
+        SV_CHECK_LAUNCH();
+        const size_t rsmem = (size_t)kRefWarps * D * sizeof(float);
+        int ctas_per_sm = (int)((200 * 1024) / (rsmem + 1024));
+        if (ctas_per_sm > 8) ctas_per_sm = 8;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        int rgrid = ta->num_sms * ctas_per_sm;
+        if (rgrid > (Nr + kRefWarps - 1) / kRefWarps) rgrid = (Nr + kRefWarps - 1) / kRefWarps;
+        knn_rescore_ref_kernel<<<rgrid, kRefWarps * 32, rsmem, st>>>(L.sel, L.inv, ta->q.x32, ta->r.x32, ta->q.norms,
+                                                                    ta->r.norms, q_row0, Nr, D);
+        SV_CHECK_LAUNCH();
+      }
       knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D);
       prof_end(rslot, st);
       SV_CHECK_LAUNCH();
@@ -1029,7 +1293,7 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
                                               q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
     } else {
-      const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : kRefineSelect);
+      const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : (loose_select() ? kRefineSelectLoose : kRefineSelect));
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, dense, row_offset, q_row0, d2_out, idx_out);
       SV_CHECK_LAUNCH();
     }
@@ -1052,7 +1316,7 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
   }
   const int n_blocks = L.n_blocks, QB = L.block_rows;
   SV_REQUIRE(n_blocks <= 64, "knn: too many query blocks (%d)", n_blocks);
-  BlockCtx ctx[2] = {{L.sel[0], L.qn, L.rn}, {L.sel[1], L.qn, L.rn}};
+  BlockCtx ctx[2] = {{L.sel[0], L.inv[0], L.qn, L.rn}, {L.sel[1], L.inv[1], L.qn, L.rn}};
   if (Nr == 0) {  // nothing to search: pad like faiss
     for (int b = 0; b < n_blocks; ++b) {
       const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
@@ -1177,6 +1441,8 @@ static int tc_setup(TcArgs& ta, const void* qbank, int Nq, const void* rbank, in
                                      (int)tc_smem_bytes<1>()));
   SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tc_smem_bytes<2>()));
+  SV_CHECK_CUDA(cudaFuncSetAttribute(knn_rescore_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kRefWarps * kRefMaxD * (int)sizeof(float)));
   return SEGVLAD_OK;
 }
 

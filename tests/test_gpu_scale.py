@@ -57,3 +57,22 @@ def test_single_cta_variant_agrees(monkeypatch):
     d2b, ib = engine.knn(qb, rb, 200)
     torch.cuda.synchronize()
     assert torch.equal(d2a, d2b) and torch.equal(ia, ib)
+
+
+def test_rescore_by_reference_row_is_bit_identical_to_the_gather(monkeypatch):
+    # final re-score through the inverted candidate lists (one warp per reference row, bank streamed once) against the
+    # per-query gather kernel: same per-lane summation order -> identical (d2, idx), incl. planted hubs (a reference row
+    # that is a candidate of MANY queries) and a D that is not a multiple of 4 (scalar path)
+    for Nq, Nr, D in [(3000, 50000, 1536), (700, 20000, 510)]:
+        q, r = synth.make_descriptor_bank(Nq, Nr, D, seed=46, planted=300, device=DEV)
+        r[123] = torch.nn.functional.normalize(q[:50].mean(0), dim=0)      # hub: near the centroid of 50 queries
+        qb, rb = engine.Bank.prepare(q), engine.Bank.prepare(r)
+        d2a, ia = engine.knn(qb, rb, 200)
+        monkeypatch.setenv("SEGVLAD_KNN_RESCORE_REF", "0")
+        d2b, ib = engine.knn(qb, rb, 200)
+        monkeypatch.delenv("SEGVLAD_KNN_RESCORE_REF")
+        torch.cuda.synchronize()
+        assert torch.equal(d2a, d2b) and torch.equal(ia, ib)
+        rows = torch.arange(0, Nq, 97, device=DEV)
+        d64, i64 = _brute_fp64(q[rows], r, 208)
+        assert_knn_close(d2a[rows].cpu().numpy(), ia[rows].cpu().numpy(), d64, i64, k_check=200)
