@@ -115,6 +115,18 @@ size_t segvlad_knn_workspace_bytes(int Nq, int Nr, int D, int k);
 int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D,
                 int k, float* d2_out, int64_t* idx_out, void* workspace, size_t workspace_bytes,
                 void* stream);
+/* Asynchronous form of segvlad_knn for pipelines (search -> [all-gather -> merge] -> vote) that must not stall the host
+ * between stages: NO host synchronisation.  `schedule` 0 = fast chunk schedule (candidate buffers can overflow on
+ * adversarially ordered / massively duplicated banks), 1 = conservative schedule (cannot overflow, slower).  The OR of the
+ * query blocks' overflow flags is written to overflow_dev (device int32, required): the caller reads it at ITS next
+ * synchronisation point (after the vote) and, if it is set, repeats the call with schedule = 1.
+ * Outputs (at least one): d2_out / idx_out as segvlad_knn, and / or topk_packed [Nq, k] uint64 =
+ * (fp32 bits of d2) << 32 | (uint32)(int32 global row) -- ascending as unsigned integers, padding = +inf | 0xffffffff --
+ * the payload of the ONE all-gather of a row-sharded search, written by the final selection kernel
+ * straight into the send buffer.  Packed output requires row_offset + Nr < 2^31 (checked on the host). */
+int segvlad_knn_async(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D, int k,
+                      int schedule, float* d2_out, int64_t* idx_out, uint64_t* topk_packed, int32_t* overflow_dev,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* Same search with both descriptor matrices in (pinned) HOST memory -- what the reference hands to faiss
  * (segFtVLAD1/2 are CPU tensors, place_rec_main.py:53-61).  The fp32 rows are copied sub-chunk by sub-chunk on a copy
  * stream straight into the banks' fp32 regions while earlier sub-chunks are split and scanned on `stream`, so the PCIe
@@ -138,6 +150,12 @@ int segvlad_knn_debug_approx(const void* qbank, int Nq, const void* rbank, int N
 /* k-way merge of per-shard results after the all-gather: parts are [G, Nq, k]. */
 int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, int Nq, int k,
                        float* d2_out, int64_t* idx_out, void* stream);
+/* The same merge on the packed all-gather payload of segvlad_knn_async: shard g's sorted lists start at
+ * parts + g * part_stride (part_stride >= Nq * k elements; the gather buffer may carry per-shard trailer words).
+ * A true k-way merge (rank by binary search, no sort, no unpacking pass); outputs d2_out / idx_out [Nq, k] (faiss
+ * layout, int64 only here) and / or packed_out [Nq, k].  G * k <= 16384. */
+int segvlad_merge_topk_packed(const uint64_t* parts, int G, size_t part_stride, int Nq, int k, float* d2_out,
+                              int64_t* idx_out, uint64_t* packed_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Vote: segment hits -> ranked reference images.

@@ -30,11 +30,14 @@ _SIGS = {
     "segvlad_bank_prepare_f64": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "segvlad_knn_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "segvlad_knn": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, C.c_size_t, _p]),
+    "segvlad_knn_async": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p,
+                                    C.c_size_t, _p]),
     "segvlad_knn_from_host": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, _p, _p,
                                         C.c_size_t, _p, _p]),
     "segvlad_knn_simt": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, C.c_size_t, _p]),
     "segvlad_knn_debug_approx": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_size_t, _p]),
     "segvlad_merge_topk": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
+    "segvlad_merge_topk_packed": (C.c_int, [_p, C.c_int, C.c_size_t, C.c_int, C.c_int, _p, _p, _p, _p]),
     "segvlad_vote_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "segvlad_vote": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, C.c_int, _p, C.c_int, C.c_int,
                                C.c_int, _p, _p, _p, _p, _p, _p, C.c_size_t, _p]),

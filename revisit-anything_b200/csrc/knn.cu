@@ -33,6 +33,9 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <map>
+#include <vector>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -582,27 +585,6 @@ enum { kRefineSelect = 0, kRefineFinal = 1, kRefineExactK = 2, kRefineSelectLoos
 constexpr int kLooseBin = 32;
 constexpr int kSmallSort = 512;   // up to this many candidates: sort them all, no selection passes
 
-// n <= 512 unique keys: every thread ranks its own keys against all others (broadcast shared-memory reads, no barriers
-// inside) and drops them at their rank -- for the ~k + margin candidates of a final pass this is about half the time of
-// the bitonic network with its log^2 barrier stages.  dst[n .. P) is padded with ~0.
-__device__ __forceinline__ void rank_sort_keys(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst,
-                                               int n, int P, int tid) {
-  for (int i = tid; i < P; i += 256) {
-    if (i >= n) { dst[i] = ~0ull; continue; }
-    const unsigned long long mine = src[i];
-    int rank = 0;
-    // keys are unique (a reference row is a candidate of a query at most once); equal keys would still be ordered by
-    // position, so the result is a permutation in any case
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) {
-      const unsigned long long o = src[j];
-      rank += (o < mine) | ((o == mine) & (j < i));
-    }
-    dst[rank] = mine;
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ void bitonic_sort_keys(unsigned long long* keys, int P, int tid) {
   for (int kk2 = 2; kk2 <= P; kk2 <<= 1) {
     for (int j = kk2 >> 1; j > 0; j >>= 1) {
@@ -622,7 +604,8 @@ __device__ __forceinline__ void bitonic_sort_keys(unsigned long long* keys, int 
 // store indices in that round).
 __global__ void __launch_bounds__(256)
 knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, long long row_offset, int q_row0,
-                  float* __restrict__ d2_out, long long* __restrict__ idx_out) {
+                  float* __restrict__ d2_out, long long* __restrict__ idx_out,
+                  unsigned long long* __restrict__ packed_out, int* __restrict__ ref_cnt, int* __restrict__ pair_total) {
   __shared__ __align__(16) unsigned s_v[kCandCap];   // d2 bit patterns   } re-used as 64-bit sort keys
   __shared__ __align__(16) int s_i[kCandCap];        // candidate rows    }
   __shared__ int s_hist[256];
@@ -638,15 +621,27 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
   if (n > kCandCap) n = kCandCap;
   float* cd = sel.cand_d2 + (size_t)row * kCandCap;
   int* ci = sel.cand_idx + (size_t)row * kCandCap;
+  // ref_cnt != nullptr (select pass before an inverted re-score): the survivors that still need the exact value are
+  // counted per reference row on the way out (first step of the list inversion, see knn_rescore_ref_kernel)
   if (mode != kRefineFinal && n <= k) {
     if (dense_first)
       for (int i = tid; i < n; i += 256) ci[i] = i;
+    if (ref_cnt) {
+      int mine = 0;
+      for (int i = tid; i < n; i += 256) {
+        const int col = dense_first ? i : ci[i];
+        if (col >= 0) { atomicAdd(ref_cnt + col, 1); ++mine; }
+      }
+      mine = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicAdd(pair_total, mine);
+    }
     return;
   }
   // Select keeps the exact-flag of a candidate; the exact modes order ties by the bare index
   const unsigned idmask = mode == kRefineSelect ? 0xffffffffu : (unsigned)~kExactFlag;
   const float twoE = mode == kRefineSelect ? 2.f * row_err_bound(em, q_row0 + row) : 0.f;
   int c = n;                       // candidates that reach the sort
+  int pending = 0;                 // this thread's survivors that still need their exact value (ref_cnt != nullptr)
   unsigned T = 0x7f800000u;        // k-th smallest d2 (bit pattern)
   int P = 1;
 
@@ -656,8 +651,7 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
       keys[i] = i < n ? (((unsigned long long)__float_as_uint(cd[i]) << 32) | ((unsigned)(dense_first ? i : ci[i]) & idmask))
                       : ~0ull;
     __syncthreads();
-    rank_sort_keys(keys, keys + kCandCap / 2, n, P, tid);
-    keys += kCandCap / 2;
+    bitonic_sort_keys(keys, P, tid);
     if (n > k) T = (unsigned)(keys[k - 1] >> 32);
     if (mode == kRefineSelect) {   // n > k here; the survivors are a prefix of the sorted list
       const unsigned keepT = __float_as_uint(__fadd_ru(__uint_as_float(T), twoE));
@@ -665,8 +659,16 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
       for (int i0 = 0; i0 < P; i0 += 256) {
         const int i = i0 + tid;
         const bool ok = i < n && (unsigned)(keys[i] >> 32) <= keepT;
-        if (ok) { cd[i] = __uint_as_float((unsigned)(keys[i] >> 32)); ci[i] = (int)(unsigned)keys[i]; }
+        if (ok) {
+          cd[i] = __uint_as_float((unsigned)(keys[i] >> 32));
+          ci[i] = (int)(unsigned)keys[i];
+          if (ref_cnt && (int)(unsigned)keys[i] >= 0) { atomicAdd(ref_cnt + (int)(unsigned)keys[i], 1); ++pending; }
+        }
         kept += __syncthreads_count(ok);
+      }
+      if (ref_cnt) {
+        pending = __reduce_add_sync(0xffffffffu, pending);
+        if (lane == 0 && pending) atomicAdd(pair_total, pending);
       }
       if (tid == 0) { sel.cnt[row] = kept; sel.tau[row] = __uint_as_float(T); }
       return;
@@ -742,7 +744,12 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
         const int pos = wbase + __popc(bal & ((1u << lane) - 1u));
         cd[pos] = __uint_as_float(v);
         ci[pos] = s_i[i];
+        if (ref_cnt && mode == kRefineSelect && s_i[i] >= 0) { atomicAdd(ref_cnt + s_i[i], 1); ++pending; }
       }
+    }
+    if (ref_cnt && mode == kRefineSelect) {
+      pending = __reduce_add_sync(0xffffffffu, pending);
+      if (lane == 0 && pending) atomicAdd(pair_total, pending);
     }
     __syncthreads();
     if (compact) {
@@ -768,12 +775,7 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
       if (i < P) keys[i] = mykeys[t];
     }
     __syncthreads();
-    if (c <= kSmallSort) {
-      rank_sort_keys(keys, keys + kCandCap / 2, c, P, tid);
-      keys += kCandCap / 2;
-    } else {
-      bitonic_sort_keys(keys, P, tid);
-    }
+    bitonic_sort_keys(keys, P, tid);
   }
   if (mode == kRefineExactK) {
     const int keep = c < k ? c : k;
@@ -784,15 +786,15 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
     if (tid == 0) sel.cnt[row] = keep;
     return;
   }
+  // final lists: (d2 fp32, global row int64) like faiss, and / or packed (d2 bits << 32 | int32 global row) -- the payload of
+  // the all-gather of a row-sharded search, written straight into the send buffer (padding: +inf | 0xffffffff)
   const size_t o = (size_t)(q_row0 + row) * k;
   for (int i = tid; i < k; i += 256) {
-    if (i < c) {
-      d2_out[o + i] = __uint_as_float((unsigned)(keys[i] >> 32));
-      idx_out[o + i] = row_offset + (long long)(unsigned)keys[i];
-    } else {
-      d2_out[o + i] = INFINITY;
-      idx_out[o + i] = -1;
-    }
+    const bool real = i < c;
+    const unsigned d2b = real ? (unsigned)(keys[i] >> 32) : 0x7f800000u;
+    const long long gi = real ? row_offset + (long long)(unsigned)keys[i] : -1ll;
+    if (d2_out) { d2_out[o + i] = __uint_as_float(d2b); idx_out[o + i] = gi; }
+    if (packed_out) packed_out[o + i] = ((unsigned long long)d2b << 32) | (unsigned)(int)gi;
   }
 }
 
@@ -806,7 +808,9 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
 // row with every warp on its own candidate maximises), two candidates per warp iteration (register pressure).
 __global__ void __launch_bounds__(256)
 knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __restrict__ r32,
-                   const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int D) {
+                   const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int D,
+                   const int* __restrict__ done_flag) {
+  if (done_flag && *done_flag) return;   // the inverted pass (knn_rescore_ref_kernel) re-scored everything
   const int row = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int n = sel.cnt[row];
   if (n > kCandCap) n = kCandCap;
@@ -854,22 +858,6 @@ constexpr int kScanTile = 4096;       // elements per CTA of the offset scan (10
 constexpr int kPairsPerRow = 512;     // pair-list capacity per query row of a block (k + margin <= this, else gather kernel)
 constexpr int kRefWarps = 8;          // warps (= reference rows in flight) per CTA of knn_rescore_ref_kernel
 constexpr int kRefMaxD = 3072;        // 8 rows x 3072 x 4 B = 96 KB of shared memory per CTA
-
-__global__ void __launch_bounds__(256)
-inv_count_kernel(SelState sel, InvState inv) {
-  const int row = blockIdx.x;
-  int n = sel.cnt[row];
-  if (n > kCandCap) n = kCandCap;
-  const int* ci = sel.cand_idx + (size_t)row * kCandCap;
-  int mine = 0;
-  for (int j = threadIdx.x; j < n; j += 256) {
-    const int col = ci[j];
-    if (col >= 0) { atomicAdd(inv.ref_off + col, 1); ++mine; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
-  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(inv.state, mine);
-}
 
 // exclusive scan of ref_off[0 .. n): per-tile scan + tile sums, scan of the tile sums (one CTA), add-back
 __global__ void __launch_bounds__(1024)
@@ -1063,6 +1051,56 @@ merge_topk_kernel(const float* __restrict__ d2p, const long long* __restrict__ i
   }
 }
 
+// k-way merge of G SORTED per-shard lists in the packed layout of the all-gather: parts[g * part_stride + row * k + j].
+// No sort: every element finds its rank in the merged order directly -- its own position j plus, for every other list,
+// the number of elements that precede it (binary search; lists with a smaller shard number win ties, which only occur
+// between padding entries because global rows are unique) -- and drops itself at that rank if it is < k.  One CTA per
+// query row, the G lists staged in shared memory.
+__global__ void __launch_bounds__(256)
+merge_packed_kernel(const unsigned long long* __restrict__ parts, int G, size_t part_stride, int Nq, int k,
+                    float* __restrict__ d2_out, long long* __restrict__ idx_out, unsigned long long* __restrict__ packed_out) {
+  extern __shared__ unsigned long long mlists[];   // [G][k]
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int n = G * k;
+  for (int i = tid; i < n; i += 256) {
+    const int g = i / k, j = i - g * k;
+    mlists[i] = parts[(size_t)g * part_stride + (size_t)row * k + j];
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += 256) {
+    const int g = i / k, j = i - g * k;
+    const unsigned long long key = mlists[i];
+    int rank = j;
+    for (int h = 0; h < G && rank < k; ++h) {
+      if (h == g) continue;
+      const unsigned long long* L = mlists + h * k;
+      // number of elements of list h ordered before (key, g): key' < key, or key' == key and h < g
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned long long v = L[mid];
+        if (v < key || (v == key && h < g)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      const size_t o = (size_t)row * k + rank;
+      if (d2_out) {
+        d2_out[o] = __uint_as_float((unsigned)(key >> 32));
+        idx_out[o] = (long long)(int)(unsigned)key;      // sign-extends the -1 of padding entries
+      }
+      if (packed_out) packed_out[o] = key;
+    }
+  }
+}
+
+__global__ void flags_or_kernel(const int* __restrict__ flags, int n, int* __restrict__ out) {
+  int v = 0;
+  for (int i = threadIdx.x; i < n; i += 32) v |= flags[i];
+  v = __reduce_or_sync(0xffffffffu, v);
+  if (threadIdx.x == 0) *out = v != 0;
+}
+
 // test hook: dense approximate scores of round 0 + the row's error bound
 __global__ void knn_debug_copy_kernel(SelState sel, ErrModel em, int q_row0, int rows, int Nr, float* __restrict__ approx_out,
                                       float* __restrict__ bound_out) {
@@ -1151,7 +1189,45 @@ static int next_chunk(int seen, int k, int Nr, bool safe) {
   return (int)c;
 }
 
+// Per-(host thread, device) context of the search: internal streams, a pool of re-usable timing-less events, the SM count
+// and the one-time kernel attributes.  Nothing here is created per call (r1: up to 512 events were created and destroyed
+// by every host-streamed search, the streams were process-wide statics bound to the first device used).
+struct DevCtx {
+  int dev = -1, num_sms = 0;
+  bool attrs_set = false, merge_attr_set = false;
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaStream_t copy = nullptr;
+  std::vector<cudaEvent_t> events;
+  int event(int i, cudaEvent_t* out) {
+    while ((int)events.size() <= i) {
+      cudaEvent_t e;
+      SV_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      events.push_back(e);
+    }
+    *out = events[i];
+    return SEGVLAD_OK;
+  }
+};
+static int dev_ctx(DevCtx** out) {
+  static thread_local std::map<int, DevCtx> ctxs;
+  int dev = 0;
+  SV_CHECK_CUDA(cudaGetDevice(&dev));
+  DevCtx& c = ctxs[dev];
+  if (c.dev < 0) {
+    SV_CHECK_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    c.dev = dev;
+  }
+  *out = &c;
+  return SEGVLAD_OK;
+}
+constexpr int kEvFork = 0, kEvJoin0 = 1, kEvJoin1 = 2, kEvHost0 = 3, kEvHostQ = 4, kEvFeed = 8;   // event pool slots
+
 struct TcArgs { BankView q, r; CUtensorMap mq, mr; int num_sms; int ctas; };
+struct KnnOut { float* d2; long long* idx; unsigned long long* packed; };   // final lists: unpacked and / or packed
+// asynchronous mode (segvlad_knn_async): no host synchronisation -- the chosen schedule runs, the OR of the query blocks'
+// overflow flags goes to overflow_dev and the caller decides (after ITS synchronisation point) whether to repeat the
+// call with the conservative schedule
+struct KnnAsync { int schedule; int* overflow_dev; };
 struct SimtArgs { const float* q; const float* r; };
 
 // Host-streamed reference bank: fp32 rows arrive from pinned host memory on a copy stream, sub-chunk by
@@ -1176,8 +1252,11 @@ static int rescore_by_ref() {
   return (e && e[0] == '0') ? 0 : 1;
 }
 static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockCtx& L, int q_row0, int rows, int Nr,
-                     int D, int k, long long row_offset, bool safe, float* d2_out, long long* idx_out,
-                     cudaStream_t st, const HostFeed* feed = nullptr) {
+                     int D, int k, long long row_offset, bool safe, const KnnOut& out, cudaStream_t st, DevCtx* dc,
+                     const HostFeed* feed = nullptr) {
+  float* d2_out = out.d2;
+  long long* idx_out = out.idx;
+  unsigned long long* packed_out = out.packed;
   // tensor-core path: filter on the approximate distances with the error-model margin, re-score exactly, keep k
   const ErrModel em = tc ? ErrModel{ta->q.meta, ta->r.stats, acc_err_const(D)} : ErrModel{nullptr, nullptr, 0.f};
   // Host-streamed bank: the GPU waits for PCIe anyway, so every sub-chunk is closed with an exact selection (select ->
@@ -1188,25 +1267,26 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
   sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel, rows, first);
   SV_CHECK_LAUNCH();
   // schedule: rounds (refine boundaries) split into sub-chunks (one filter launch each)
-  SubChunk sched[512];
+  std::vector<SubChunk> sched;
   int ns = 0;
   for (int seen = 0; seen < Nr;) {
     const int chunk = next_chunk(seen, k, Nr, safe);
     for (int s0 = seen; s0 < seen + chunk;) {
-      SV_REQUIRE(ns < 512, "knn: schedule too long");
       // host-streamed: the last rows arrive in small pieces so that little work is left when the copy ends
       int sub = chunk;
       if (feed && seen > 0) sub = (Nr - s0 <= feed->sub_rows) ? (feed->sub_rows / 2 > kTileN ? feed->sub_rows / 2 : kTileN) : feed->sub_rows;
       const int s1 = (s0 + sub < seen + chunk) ? s0 + sub : seen + chunk;
-      sched[ns++] = {s0, s1, seen == 0, incremental || s1 == seen + chunk, s1 == Nr};
+      sched.push_back({s0, s1, seen == 0, incremental || s1 == seen + chunk, s1 == Nr});
+      ++ns;
       s0 = s1;
     }
     seen += chunk;
   }
-  cudaEvent_t ev[512];
+  std::vector<cudaEvent_t> ev(feed ? ns : 0);
   if (feed) {
     for (int i = 0; i < ns; ++i) {
-      SV_CHECK_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+      const int erc = dc->event(kEvFeed + i, &ev[i]);     // pooled: created once per (thread, device), never per call
+      if (erc) return erc;
       const size_t off = (size_t)sched[i].c0 * D, cnt = (size_t)(sched[i].c1 - sched[i].c0) * D;
       SV_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(ta->r.x32) + off, feed->r_host + off, cnt * sizeof(float),
                                     cudaMemcpyHostToDevice, feed->copy));
@@ -1254,20 +1334,25 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     const bool final_pass = sched[i].final_pass != 0;
     const int dense = (tc && first_round) ? 1 : 0;   // round 0 of the tensor-core filter stores scores only
     if (tc && (safe || incremental || final_pass)) {
-      // approximate selection (prunes to ~k + margin), exact re-score of what is not exact yet, exact selection
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, dense, row_offset, q_row0, d2_out, idx_out);
-      SV_CHECK_LAUNCH();
-      const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
-      // final pass of a resident search: every row has ~k + margin candidates to re-score -> by reference row (the bank
-      // streams from HBM once); sub-chunk passes (host-streamed / conservative schedule) re-score few NEW survivors ->
-      // gather kernel.  The gather kernel also runs after the inverted pass: it skips what is exact already, i.e. it
-      // is a no-op unless the pair lists did not fit (state[1] == 0, decided on the device).
-      if (final_pass && !incremental && !safe && rescore_by_ref() && D <= kRefMaxD && Nr >= 4 * kScanTile) {
-        const int n_tiles = (Nr + kScanTile - 1) / kScanTile;
+      // approximate selection (prunes to ~k + margin), exact re-score of what is not exact yet, exact selection.
+      // Final pass of a resident search: every row has ~k + margin candidates to re-score -> by reference row (the bank
+      // streams from HBM once; the select pass counts the survivors per reference row on its way out); sub-chunk passes
+      // (host-streamed / conservative schedule) re-score few NEW survivors -> gather kernel.  The gather kernel is also
+      // launched after the inverted pass and returns at once unless the pair lists did not fit (state[1] == 0, decided
+      // on the device).
+      const bool by_ref = final_pass && !incremental && !safe && rescore_by_ref() && D <= kRefMaxD && Nr >= 4 * kScanTile;
+      int* inv_cnt = by_ref ? L.inv.ref_off : nullptr;
+      int* inv_tot = by_ref ? L.inv.state : nullptr;
+      if (by_ref) {
         SV_CHECK_CUDA(cudaMemsetAsync(L.inv.ref_off, 0, sizeof(int) * ((size_t)Nr + 1), st));
         SV_CHECK_CUDA(cudaMemsetAsync(L.inv.state, 0, sizeof(int) * 4, st));
-        inv_count_kernel<<<rows, 256, 0, st>>>(L.sel, L.inv);
-        SV_CHECK_LAUNCH();
+      }
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, kRefineSelect, dense, row_offset, q_row0, d2_out, idx_out,
+                                              packed_out, inv_cnt, inv_tot);
+      SV_CHECK_LAUNCH();
+      const int rslot = prof_begin(SEGVLAD_PROF_KNN_RESCORE, st);
+      if (by_ref) {
+        const int n_tiles = (Nr + kScanTile - 1) / kScanTile;
         inv_scan_tiles_kernel<<<n_tiles, 1024, 0, st>>>(L.inv, Nr);
         SV_CHECK_LAUNCH();
         inv_scan_sums_kernel<<<1, 1024, 0, st>>>(L.inv, n_tiles);
@@ -1286,28 +1371,31 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
                                                                     ta->r.norms, q_row0, Nr, D);
         SV_CHECK_LAUNCH();
       }
-      knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D);
+      knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D,
+                                               by_ref ? L.inv.state + 1 : nullptr);
       prof_end(rslot, st);
       SV_CHECK_LAUNCH();
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, final_pass ? kRefineFinal : kRefineExactK, 0, row_offset,
-                                              q_row0, d2_out, idx_out);
+                                              q_row0, d2_out, idx_out, packed_out, nullptr, nullptr);
       SV_CHECK_LAUNCH();
     } else {
       const int mode = final_pass ? kRefineFinal : (safe ? kRefineExactK : (loose_select() ? kRefineSelectLoose : kRefineSelect));
-      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, dense, row_offset, q_row0, d2_out, idx_out);
+      knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel, em, k, mode, dense, row_offset, q_row0, d2_out, idx_out, packed_out,
+                                              nullptr, nullptr);
       SV_CHECK_LAUNCH();
     }
   }
-  if (feed)
-    for (int i = 0; i < ns; ++i) cudaEventDestroy(ev[i]);
   return SEGVLAD_OK;
 }
 
 static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, int D, int k, long long row_offset,
-                      float* d2_out, long long* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t st,
-                      const HostFeed* feed = nullptr) {
+                      const KnnOut& out, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                      const HostFeed* feed = nullptr, const KnnAsync* as = nullptr) {
   SV_REQUIRE(Nq >= 0 && Nr >= 0 && D > 0, "knn: bad shape");
   SV_REQUIRE(k > 0 && k <= kMaxK, "knn: k must be in [1, %d] (got %d)", kMaxK, k);
+  SV_REQUIRE((out.d2 != nullptr) == (out.idx != nullptr) && (out.d2 || out.packed), "knn: no output buffer");
+  SV_REQUIRE(!out.packed || row_offset + (long long)Nr <= 0x7fffffffll, "knn: packed output needs global rows < 2^31");
+  if (as && as->overflow_dev) SV_CHECK_CUDA(cudaMemsetAsync(as->overflow_dev, 0, sizeof(int), st));
   if (Nq == 0) return SEGVLAD_OK;
   KnnLayout L = carve_knn(workspace, Nq, Nr);
   if (!workspace || workspace_bytes < L.total) {
@@ -1316,6 +1404,8 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
   }
   const int n_blocks = L.n_blocks, QB = L.block_rows;
   SV_REQUIRE(n_blocks <= 64, "knn: too many query blocks (%d)", n_blocks);
+  DevCtx* dc = nullptr;
+  { const int rc = dev_ctx(&dc); if (rc) return rc; }
   BlockCtx ctx[2] = {{L.sel[0], L.inv[0], L.qn, L.rn}, {L.sel[1], L.inv[1], L.qn, L.rn}};
   if (Nr == 0) {  // nothing to search: pad like faiss
     for (int b = 0; b < n_blocks; ++b) {
@@ -1323,7 +1413,7 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
       sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel[0], rows, 0);
       SV_CHECK_LAUNCH();
       knn_refine_kernel<<<rows, 256, 0, st>>>(L.sel[0], ErrModel{nullptr, nullptr, 0.f}, k, kRefineFinal, 0, row_offset, q0,
-                                              d2_out, idx_out);
+                                              out.d2, out.idx, out.packed, nullptr, nullptr);
       SV_CHECK_LAUNCH();
     }
     return SEGVLAD_OK;
@@ -1334,42 +1424,50 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
     row_norms_kernel<<<(Nr + 7) / 8, 256, 0, st>>>(sa->r, Nr, D, L.rn);
     SV_CHECK_LAUNCH();
   }
-  // two internal streams when there are >= 2 query blocks and the bank is already resident
-  static cudaStream_t aux[2] = {nullptr, nullptr};
+  // two internal streams when there are >= 2 query blocks and the bank is already resident (development switch)
   const char* denv = getenv("SEGVLAD_KNN_DUAL");
   const bool dual = n_blocks >= 2 && feed == nullptr && denv && denv[0] == '1';
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   if (dual) {
     for (int i = 0; i < 2; ++i)
-      if (!aux[i]) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
-    SV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      if (!dc->aux[i]) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&dc->aux[i], cudaStreamNonBlocking));
+    int rc = dc->event(kEvFork, &ev_fork);
+    if (!rc) rc = dc->event(kEvJoin0, &ev_join[0]);
+    if (!rc) rc = dc->event(kEvJoin1, &ev_join[1]);
+    if (rc) return rc;
     SV_CHECK_CUDA(cudaEventRecord(ev_fork, st));
-    for (int i = 0; i < 2; ++i) SV_CHECK_CUDA(cudaStreamWaitEvent(aux[i], ev_fork, 0));
+    for (int i = 0; i < 2; ++i) SV_CHECK_CUDA(cudaStreamWaitEvent(dc->aux[i], ev_fork, 0));
   }
+  const bool first_safe = as && as->schedule == 1;
   for (int b = 0; b < n_blocks; ++b) {
     const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
     const int si = dual ? (b & 1) : 0;
-    cudaStream_t bs = dual ? aux[si] : st;
-    int rc = run_block(tc, ta, sa, ctx[si], q0, rows, Nr, D, k, row_offset, false, d2_out, idx_out, bs,
+    cudaStream_t bs = dual ? dc->aux[si] : st;
+    int rc = run_block(tc, ta, sa, ctx[si], q0, rows, Nr, D, k, row_offset, first_safe, out, bs, dc,
                        b == 0 ? feed : nullptr);   // after the first query block the bank is resident
     if (rc) return rc;
     SV_CHECK_CUDA(cudaMemcpyAsync(L.flags + b, ctx[si].sel.overflow, sizeof(int), cudaMemcpyDeviceToDevice, bs));
   }
   if (dual) {
     for (int i = 0; i < 2; ++i) {
-      SV_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
-      SV_CHECK_CUDA(cudaEventRecord(ev_join[i], aux[i]));
+      SV_CHECK_CUDA(cudaEventRecord(ev_join[i], dc->aux[i]));
       SV_CHECK_CUDA(cudaStreamWaitEvent(st, ev_join[i], 0));
     }
+  }
+  if (as) {   // asynchronous contract: publish the flag, never touch the host
+    if (as->overflow_dev) {
+      flags_or_kernel<<<1, 32, 0, st>>>(L.flags, n_blocks, as->overflow_dev);
+      SV_CHECK_LAUNCH();
+    }
+    return SEGVLAD_OK;
   }
   int hflags[64];
   SV_CHECK_CUDA(cudaMemcpyAsync(hflags, L.flags, sizeof(int) * n_blocks, cudaMemcpyDeviceToHost, st));
   SV_CHECK_CUDA(cudaStreamSynchronize(st));
-  if (dual) { cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join[0]); cudaEventDestroy(ev_join[1]); }
   for (int b = 0; b < n_blocks; ++b) {
     if (!hflags[b]) continue;
     const int q0 = b * QB, rows = (Nq - q0) < QB ? (Nq - q0) : QB;
-    int rc = run_block(tc, ta, sa, ctx[0], q0, rows, Nr, D, k, row_offset, true, d2_out, idx_out, st);
+    int rc = run_block(tc, ta, sa, ctx[0], q0, rows, Nr, D, k, row_offset, true, out, st, dc);
     if (rc) return rc;
     int f = 0;
     SV_CHECK_CUDA(cudaMemcpyAsync(&f, ctx[0].sel.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1434,15 +1532,18 @@ static int tc_setup(TcArgs& ta, const void* qbank, int Nq, const void* rbank, in
   const int r_box = ta.ctas == 2 ? kTileN / 2 : kTileN;
   if ((rc = make_map(&ta.mq, ta.q.h16, Nq, ta.q.Dp, kTileM))) return rc;
   if ((rc = make_map(&ta.mr, ta.r.h16, Nr, ta.r.Dp, r_box))) return rc;
-  int dev = 0;
-  SV_CHECK_CUDA(cudaGetDevice(&dev));
-  SV_CHECK_CUDA(cudaDeviceGetAttribute(&ta.num_sms, cudaDevAttrMultiProcessorCount, dev));
-  SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc_smem_bytes<1>()));
-  SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc_smem_bytes<2>()));
-  SV_CHECK_CUDA(cudaFuncSetAttribute(knn_rescore_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kRefWarps * kRefMaxD * (int)sizeof(float)));
+  DevCtx* dc = nullptr;
+  if ((rc = dev_ctx(&dc))) return rc;
+  ta.num_sms = dc->num_sms;
+  if (!dc->attrs_set) {   // once per (thread, device)
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes<1>()));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes<2>()));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_rescore_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kRefWarps * kRefMaxD * (int)sizeof(float)));
+    dc->attrs_set = true;
+  }
   return SEGVLAD_OK;
 }
 
@@ -1455,8 +1556,25 @@ extern "C" int segvlad_knn(const void* qbank, int Nq, const void* rbank, int Nr,
     int rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
     if (rc) return rc;
   }
-  return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
-                    workspace, workspace_bytes, st);
+  const KnnOut out{d2_out, reinterpret_cast<long long*>(idx_out), nullptr};
+  return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, out, workspace, workspace_bytes, st);
+}
+
+extern "C" int segvlad_knn_async(const void* qbank, int Nq, const void* rbank, int Nr, int64_t row_offset, int D, int k,
+                                 int schedule, float* d2_out, int64_t* idx_out, uint64_t* topk_packed,
+                                 int32_t* overflow_dev, void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(D > 0, "knn_async: bad D");
+  SV_REQUIRE(schedule == 0 || schedule == 1, "knn_async: schedule must be 0 (fast) or 1 (conservative)");
+  SV_REQUIRE(overflow_dev != nullptr, "knn_async: overflow_dev is required (the caller must check it)");
+  TcArgs ta;
+  if (Nq > 0 && Nr > 0) {
+    int rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
+    if (rc) return rc;
+  }
+  const KnnOut out{d2_out, reinterpret_cast<long long*>(idx_out), reinterpret_cast<unsigned long long*>(topk_packed)};
+  const KnnAsync as{schedule, overflow_dev};
+  return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, out, workspace, workspace_bytes, st, nullptr, &as);
 }
 
 extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r_host, int Nr, int64_t row_offset, int D,
@@ -1466,19 +1584,30 @@ extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r
   SV_REQUIRE(D > 0 && Nq > 0 && Nr > 0 && q_host && r_host && qbank && rbank, "knn_from_host: bad arguments");
   SV_REQUIRE((reinterpret_cast<uintptr_t>(qbank) & 255) == 0 && (reinterpret_cast<uintptr_t>(rbank) & 255) == 0,
              "knn_from_host: banks must be 256-byte aligned");
-  static cudaStream_t own_copy = nullptr;
+  // everything that can fail on the arguments is checked before any work is enqueued
+  SV_REQUIRE(k > 0 && k <= kMaxK, "knn_from_host: k must be in [1, %d] (got %d)", kMaxK, k);
+  {
+    const KnnLayout Lc = carve_knn(nullptr, Nq, Nr);
+    if (!workspace || workspace_bytes < Lc.total) {
+      set_error("knn_from_host: workspace %zu < required %zu", workspace_bytes, Lc.total);
+      return SEGVLAD_EWORKSPACE;
+    }
+    SV_REQUIRE(Lc.n_blocks <= 64, "knn_from_host: too many query blocks (%d)", Lc.n_blocks);
+  }
+  DevCtx* dc = nullptr;
+  int rc = dev_ctx(&dc);
+  if (rc) return rc;
   cudaStream_t cp = reinterpret_cast<cudaStream_t>(copy_stream_);
   if (!cp) {
-    if (!own_copy) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&own_copy, cudaStreamNonBlocking));
-    cp = own_copy;
+    if (!dc->copy) SV_CHECK_CUDA(cudaStreamCreateWithFlags(&dc->copy, cudaStreamNonBlocking));
+    cp = dc->copy;
   }
   TcArgs ta;
-  int rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
+  rc = tc_setup(ta, qbank, Nq, rbank, Nr, D);
   if (rc) return rc;
   // order the copy stream after everything already queued on the compute stream (buffer re-use across calls)
   cudaEvent_t e0, eq;
-  SV_CHECK_CUDA(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
-  SV_CHECK_CUDA(cudaEventCreateWithFlags(&eq, cudaEventDisableTiming));
+  if ((rc = dc->event(kEvHost0, &e0)) || (rc = dc->event(kEvHostQ, &eq))) return rc;
   SV_CHECK_CUDA(cudaEventRecord(e0, st));
   SV_CHECK_CUDA(cudaStreamWaitEvent(cp, e0, 0));
   SV_CHECK_CUDA(cudaMemcpyAsync(const_cast<float*>(ta.q.x32), q_host, sizeof(float) * (size_t)Nq * D,
@@ -1489,12 +1618,12 @@ extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r
   SV_CHECK_CUDA(cudaMemsetAsync(const_cast<unsigned*>(ta.r.stats), 0, 64 * sizeof(unsigned), st));
   bank_prepare_rows_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(0, Nq, D, bank_out(ta.q));
   SV_CHECK_LAUNCH();
-  HostFeed feed{r_host, cp, 8192};
-  rc = knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out), workspace,
-                  workspace_bytes, st, &feed);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(eq);
-  return rc;
+  // copy / scan sub-chunks of 8192 rows; banks beyond ~3 M rows use proportionally larger ones (<= ~400 sub-chunks)
+  int sub_rows = 8192;
+  while ((long long)sub_rows * 384 < Nr) sub_rows *= 2;
+  HostFeed feed{r_host, cp, sub_rows};
+  const KnnOut out{d2_out, reinterpret_cast<long long*>(idx_out), nullptr};
+  return knn_driver(true, &ta, nullptr, Nq, Nr, D, k, row_offset, out, workspace, workspace_bytes, st, &feed);
 }
 
 extern "C" int segvlad_knn_debug_approx(const void* qbank, int Nq, const void* rbank, int Nr, int D, float* approx_out,
@@ -1547,8 +1676,8 @@ extern "C" int segvlad_knn_simt(const float* q, int Nq, const float* r, int Nr, 
                                 void* stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   SimtArgs sa{q, r};
-  return knn_driver(false, nullptr, &sa, Nq, Nr, D, k, row_offset, d2_out, reinterpret_cast<long long*>(idx_out),
-                    workspace, workspace_bytes, st);
+  const KnnOut out{d2_out, reinterpret_cast<long long*>(idx_out), nullptr};
+  return knn_driver(false, nullptr, &sa, Nq, Nr, D, k, row_offset, out, workspace, workspace_bytes, st);
 }
 
 extern "C" int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_parts, int G, int Nq, int k, float* d2_out,
@@ -1563,6 +1692,28 @@ extern "C" int segvlad_merge_topk(const float* d2_parts, const int64_t* idx_part
   SV_CHECK_CUDA(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
   merge_topk_kernel<<<Nq, 256, smem, st>>>(d2_parts, reinterpret_cast<const long long*>(idx_parts), G, Nq, k, d2_out,
                                            reinterpret_cast<long long*>(idx_out));
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+extern "C" int segvlad_merge_topk_packed(const uint64_t* parts, int G, size_t part_stride, int Nq, int k, float* d2_out,
+                                         int64_t* idx_out, uint64_t* packed_out, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(G > 0 && Nq >= 0 && k > 0 && parts, "merge_topk_packed: bad arguments");
+  SV_REQUIRE(part_stride >= (size_t)Nq * k, "merge_topk_packed: part_stride < Nq * k");
+  SV_REQUIRE((d2_out != nullptr) == (idx_out != nullptr) && (d2_out || packed_out), "merge_topk_packed: no output buffer");
+  SV_REQUIRE((long long)G * k <= 16384, "merge_topk_packed: G*k must be <= 16384 (got %lld)", (long long)G * k);
+  if (Nq == 0) return SEGVLAD_OK;
+  const size_t smem = (size_t)G * k * 8;
+  DevCtx* dc = nullptr;
+  { const int rc = dev_ctx(&dc); if (rc) return rc; }
+  if (!dc->merge_attr_set) {
+    SV_CHECK_CUDA(cudaFuncSetAttribute(merge_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    dc->merge_attr_set = true;
+  }
+  merge_packed_kernel<<<Nq, 256, smem, st>>>(reinterpret_cast<const unsigned long long*>(parts), G, part_stride, Nq, k, d2_out,
+                                            reinterpret_cast<long long*>(idx_out),
+                                            reinterpret_cast<unsigned long long*>(packed_out));
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }

@@ -183,6 +183,43 @@ def knn(q: Bank, r: Bank, k: int, row_offset: int = 0) -> Tuple[torch.Tensor, to
     return d2, idx
 
 
+def knn_async(q: Bank, r: Bank, k: int, row_offset: int = 0, schedule: int = 0, packed_out: Optional[torch.Tensor] = None,
+              overflow: Optional[torch.Tensor] = None, unpacked: bool = True):
+    """segvlad_knn_async: the same search with NO host synchronisation.  Returns (d2, idx, overflow): `overflow` is a
+    device int32[1] the caller must read at its next synchronisation point (after the vote); if it is non-zero the
+    candidate buffers overflowed under the fast schedule and the call has to be repeated with schedule=1.
+    packed_out: optional int64 CUDA tensor with >= Nq*k elements that receives the packed lists
+    ((fp32 bits of d2) << 32 | uint32(int32 global row)) -- e.g. this rank's slot of the all-gather buffer."""
+    assert q.D == r.D
+    dev = q.buf.device
+    d2 = torch.empty((q.n, k), dtype=torch.float32, device=dev) if unpacked else None
+    idx = torch.empty((q.n, k), dtype=torch.int64, device=dev) if unpacked else None
+    if overflow is None:
+        overflow = torch.empty(1, dtype=torch.int32, device=dev)
+    if packed_out is not None:
+        assert packed_out.is_cuda and packed_out.dtype == torch.int64 and packed_out.is_contiguous()
+        assert packed_out.numel() >= q.n * k
+    ws = _ws(lib().segvlad_knn_workspace_bytes(q.n, r.n, q.D, k), dev)
+    check(lib().segvlad_knn_async(_ptr(q.buf), q.n, _ptr(r.buf), r.n, int(row_offset), q.D, k, int(schedule), _ptr(d2),
+                                  _ptr(idx), _ptr(packed_out), _ptr(overflow), _ptr(ws), ws.numel(), _stream()),
+          "segvlad_knn_async")
+    return d2, idx, overflow
+
+
+def merge_topk_packed(parts: torch.Tensor, Nq: int, k: int, want_packed: bool = False):
+    """parts: int64 CUDA [G, stride] (stride >= Nq*k), shard g's sorted packed lists at parts[g, :Nq*k] (the gathered
+    buffer of the row-sharded search) -> merged (d2 [Nq,k] fp32, idx [Nq,k] int64) (+ packed [Nq,k] int64)."""
+    _need_cuda(parts)
+    assert parts.dtype == torch.int64 and parts.is_contiguous() and parts.dim() == 2 and parts.shape[1] >= Nq * k
+    G, stride = parts.shape
+    d2 = torch.empty((Nq, k), dtype=torch.float32, device=parts.device)
+    idx = torch.empty((Nq, k), dtype=torch.int64, device=parts.device)
+    packed = torch.empty((Nq, k), dtype=torch.int64, device=parts.device) if want_packed else None
+    check(lib().segvlad_merge_topk_packed(_ptr(parts), G, stride, Nq, k, _ptr(d2), _ptr(idx), _ptr(packed), _stream()),
+          "segvlad_merge_topk_packed")
+    return (d2, idx, packed) if want_packed else (d2, idx)
+
+
 def knn_from_host(q_host: torch.Tensor, r_host: torch.Tensor, k: int, row_offset: int = 0, device=None):
     """Search with both fp32 descriptor matrices in host memory (pin them for full PCIe rate): the H2D transfer
     of the reference bank is pipelined with the tensor-core scan.  Returns (d2, idx, qbank, rbank) -- the banks are

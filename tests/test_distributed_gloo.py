@@ -15,7 +15,7 @@ from revisit_anything_b200 import distributed as D
 from revisit_anything_b200 import synth
 
 
-class OracleOps:
+class OracleOps(D.OpsBase):
     def prepare(self, x):
         return x
 
@@ -72,7 +72,9 @@ def test_shard_bounds():
 def test_pack_roundtrip():
     d2 = torch.tensor([[0.0, 1.5, float("inf")]], dtype=torch.float32)
     idx = torch.tensor([[7, 2 ** 31 - 1, -1]], dtype=torch.int64)
-    a, b = D.unpack_topk(D.pack_topk(d2, idx))
+    keys = D.pack_topk(d2, idx)
+    assert bool((keys[0, 1:] > keys[0, :-1]).all())             # sorted lists stay sorted as integer keys; padding is last
+    a, b = D.unpack_topk(keys)
     assert torch.equal(a, d2) and torch.equal(b, idx)
     with pytest.raises(ValueError):
         D.pack_topk(d2, torch.tensor([[2 ** 31, 0, 0]], dtype=torch.int64))

@@ -136,6 +136,77 @@ def test_merge_topk_with_shards_shorter_than_k():
             assert (mi.cpu().numpy()[:, n:] == -1).all() and np.isinf(md.cpu().numpy()[:, n:]).all()
 
 
+def test_async_search_packed_output_and_overflow_flag():
+    # segvlad_knn_async: no host synchronisation, packed (d2 bits << 32 | int32 global row) lists for the all-gather, the
+    # overflow flag published on the device; identical lists to the synchronous call
+    from revisit_anything_b200 import distributed as Dm
+    q, r = synth.make_descriptor_bank(300, 21000, 192, seed=12, planted=50, device=DEV)
+    qb, rb = engine.Bank.prepare(q), engine.Bank.prepare(r)
+    k, off = 200, 1_000_000
+    d2s, idxs = engine.knn(qb, rb, k, row_offset=off)
+    payload = torch.full((300 * k + Dm.TRAILER,), -7, dtype=torch.int64, device=DEV)
+    d2a, idxa, flag = engine.knn_async(qb, rb, k, off, schedule=0, packed_out=payload)
+    torch.cuda.synchronize()
+    assert int(flag.item()) == 0
+    assert torch.equal(d2a, d2s) and torch.equal(idxa, idxs)
+    assert torch.equal(payload[:300 * k].view(300, k).cpu(), Dm.pack_topk(d2s.cpu(), idxs.cpu()))
+    assert bool((payload[300 * k:] == -7).all())                 # nothing written behind the lists
+    for sched in (0, 1):                                         # packed-only mode, both schedules
+        p2 = torch.empty(300 * k, dtype=torch.int64, device=DEV)
+        a, b, f2 = engine.knn_async(qb, rb, k, off, schedule=sched, packed_out=p2, unpacked=False)
+        torch.cuda.synchronize()
+        assert a is None and b is None and int(f2.item()) == 0 and torch.equal(p2, payload[:300 * k])
+    with pytest.raises(ValueError):                              # int32 bound of the packed rows is a host-side check
+        engine.knn_async(qb, rb, k, 2 ** 31 - 100, packed_out=payload)
+    # adversarial order (test above): the fast schedule must raise the flag, the conservative one must not and be exact
+    g = torch.Generator(device=DEV).manual_seed(0)
+    D, Nr, Nq = 64, 30000, 130
+    base = torch.nn.functional.normalize(torch.randn(1, D, generator=g, device=DEV), dim=1)
+    noise = torch.nn.functional.normalize(torch.randn(Nr, D, generator=g, device=DEV), dim=1)
+    a = torch.linspace(0.05, 0.95, Nr, device=DEV)[:, None]
+    r = torch.nn.functional.normalize(a * base + (1 - a) * 0.3 * noise, dim=1)
+    q = torch.nn.functional.normalize(base + 0.01 * torch.randn(Nq, D, generator=g, device=DEV), dim=1)
+    qb, rb = engine.Bank.prepare(q), engine.Bank.prepare(r)
+    _, _, f0 = engine.knn_async(qb, rb, 200, 0, schedule=0)
+    d2c, idxc, f1 = engine.knn_async(qb, rb, 200, 0, schedule=1)
+    torch.cuda.synchronize()
+    assert int(f0.item()) == 1 and int(f1.item()) == 0
+    d2s, idxs = engine.knn(qb, rb, 200)
+    assert torch.equal(d2c, d2s) and torch.equal(idxc, idxs)
+    # the host-side pipeline repeats the step by itself when the flag is set
+    ops = Dm.EngineOps()
+    qoff = torch.tensor([0, 60, 130], dtype=torch.int32, device=DEV)
+    rimg = (torch.arange(Nr, device=DEV) // 100).to(torch.int32)
+    d2p, idxp, preds = Dm.sharded_search_and_vote(ops, qb, rb, 0, qoff, rimg, 300, 200, 50, 5)
+    assert torch.equal(d2p, d2s) and torch.equal(idxp, idxs)
+    assert torch.equal(preds, ops.vote(idxs, d2s, qoff, rimg, 300, 5, 50))
+
+
+def test_merge_packed_is_the_same_k_way_merge():
+    # packed gather buffer (with trailer words) -> rank-by-binary-search merge; against the unpacked sort-based merge and
+    # the single-shard search, incl. shards shorter than k (padding) and an exact cross-shard tie
+    from revisit_anything_b200 import distributed as Dm
+    q, r = synth.make_descriptor_bank(130, 700, 128, seed=9, planted=20, device=DEV)
+    r[10] = r[400]
+    k = 200
+    qb = engine.Bank.prepare(q)
+    for bounds in ([0, 60, 150, 700], [0, 50, 120, 180], [0, 350, 700]):
+        n, G = bounds[-1], len(bounds) - 1
+        d2_full, idx_full = engine.knn(qb, engine.Bank.prepare(r[:n]), k)
+        buf = torch.zeros((G, 130 * k + Dm.TRAILER), dtype=torch.int64, device=DEV)
+        pd, pi = [], []
+        for g in range(G):
+            d, i, _ = engine.knn_async(qb, engine.Bank.prepare(r[bounds[g]:bounds[g + 1]]), k, bounds[g], packed_out=buf[g])
+            pd.append(d)
+            pi.append(i)
+        md, mi, mp = engine.merge_topk_packed(buf, 130, k, want_packed=True)
+        md2, mi2 = engine.merge_topk(torch.stack(pd), torch.stack(pi))
+        torch.cuda.synchronize()
+        assert torch.equal(md, d2_full) and torch.equal(mi, idx_full)
+        assert torch.equal(md, md2) and torch.equal(mi, mi2)
+        assert torch.equal(mp.cpu(), Dm.pack_topk(md.cpu(), mi.cpu()))
+
+
 def test_bank_prepare_f64_normalizes_like_normalizeFeat():
     g = torch.Generator().manual_seed(3)
     x = torch.randn(500, 200, generator=g, dtype=torch.float64) * 3.0
