@@ -447,22 +447,16 @@ def config1_leg(device, n_img=406, oracle_imgs=24, pca_dim=1024):
             masks = synth.jitter_masks(masks, i, 4)
         return tok, masks
 
-    t_adj = [0.0]
-
     def build(query):
         descs, im_inds, t_host, t_gpu, n_seg = [], [], 0.0, 0.0, 0
         for b0 in range(0, n_img, 16):
             t0 = time.perf_counter()
             items = [image(i, query) for i in range(b0, min(n_img, b0 + 16))]
             t_host += time.perf_counter() - t0
-            t0 = time.perf_counter()
-            adjs = [func_vpr.nbrMasksAGGFastSingle(m, order) for _, m in items]    # host (scipy Qhull), as in the reference
-            t_adj[0] += time.perf_counter() - t0
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             d, im = place_rec_main.build_segment_descriptors([t for t, _ in items], [m for _, m in items], centers, cfg,
-                                                             order, desc_dim=D, batch_images=16, adjacency=adjs,
-                                                             pca_model_path=tmp.name)
+                                                             order, desc_dim=D, batch_images=16, pca_model_path=tmp.name)
             torch.cuda.synchronize()
             t_gpu += time.perf_counter() - t0
             descs.append(d)
@@ -511,10 +505,11 @@ def config1_leg(device, n_img=406, oracle_imgs=24, pca_dim=1024):
                     f"order {order}, K={K}, PCA {K * D}->{pca_dim} (synthetic whitening model), vocabulary: "
                     + ("reference indoor/c_centers.pt" if real_vocab else "seeded synthetic"),
         "images": 2 * n_img, "superseg": int(ns1 + ns2),
-        "aggregate_pca_s": tg1 + tg2, "host_adjacency_s": t_adj[0], "host_synth_s": th1 + th2, "match_vote_s": t_match,
+        "aggregate_pca_s": tg1 + tg2, "host_synth_s": th1 + th2, "match_vote_s": t_match,
         "images_per_s": 2 * n_img / (tg1 + tg2), "superseg_per_s": (ns1 + ns2) / (tg1 + tg2),
-        "aggregate_pca_note": "token / mask upload + membership + SuperSegment union + aggregation + PCA projection per 16-image "
-                              "batch; the Delaunay adjacency (scipy on the host, as in the reference) is timed apart",
+        "aggregate_pca_note": "host tokens + masks -> device descriptors per 16-image batch: uploads, membership + mask centroids "
+                              "(GPU), Delaunay adjacency (scipy on the host, as in the reference), SuperSegment union, "
+                              "aggregation, PCA projection",
         "recall_at_1_5": recalls,
         "parity": {"images": m, "recall_kernel": k_rec, "recall_oracle": o_rec, "recalls_equal": k_rec == o_rec,
                    "predictions_equal": [list(map(int, a)) for a in k_preds] == [list(map(int, b)) for b in o_preds],
@@ -551,6 +546,38 @@ def identity_check(ops, engine, D, rank, world, device, d, rows_per_rank=8192, n
             "preds_identical": ok[2], "what": "merged per-shard top-k + vote == single-GPU search + vote of the same bank, on every rank"}
 
 
+def write_trace(path, step, rank, barrier):
+    """GPU timeline of two resident steps through torch.profiler (CUPTI): every kernel / copy of this rank with its start
+    offset and duration -- the N > 1 counterpart of the ncu launch list (ncu must not wrap a multi-rank command, nsys is
+    not in the image).  Profiling perturbs the timing; the JSON line's numbers never come from a traced run."""
+    import tempfile
+
+    from torch.profiler import ProfilerActivity, profile
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+    barrier()
+    if rank != 0:
+        return
+    tmp = tempfile.NamedTemporaryFile(suffix=".json", delete=False)
+    tmp.close()
+    prof.export_chrome_trace(tmp.name)
+    ev = [e for e in json.load(open(tmp.name)).get("traceEvents", [])
+          if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+    os.unlink(tmp.name)
+    ev.sort(key=lambda e: e["ts"])
+    if not ev:
+        return
+    t0 = ev[0]["ts"]
+    with open(path, "w") as fh:
+        fh.write("# start_us  dur_us  stream  name   (two resident steps, rank 0; torch.profiler / CUPTI)\n")
+        for e in ev:
+            fh.write(f"{e['ts'] - t0:10.1f} {e['dur']:9.1f}  {e.get('args', {}).get('stream', '?'):>4}  {e['name'][:110]}\n")
+        fh.write(f"# span {ev[-1]['ts'] + ev[-1]['dur'] - t0:.1f} us, sum of durations {sum(e['dur'] for e in ev):.1f} us\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -565,6 +592,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aggregation", action="store_true", help="(kept from r1) same as --legs none")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace", default=None, help="write a GPU timeline (kernels + copies, rank 0) of two resident steps here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -644,6 +672,9 @@ def main():
     rescore_ms, _ = _prof(lib, 3)
     lib.segvlad_profile_enable(0)
     lib.segvlad_profile_reset()
+
+    if args.trace:
+        write_trace(args.trace, step_resident, rank, barrier)
 
     pairs_step = NQ * NR * world
     ms_step = ms_total / args.steps

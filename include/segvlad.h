@@ -91,6 +91,10 @@ int segvlad_aggregate_residuals(const float* residuals, const int32_t* labels, i
  *  is a member if any pixel of its (clipped) patch x patch cell is set.  member_bits [S, ceil(N/32)]. */
 int segvlad_mask_to_membership(const uint8_t* masks, int S, int Hm, int Wm, int H, int W, int patch,
                                uint32_t* member_bits, void* stream);
+/* Mask centroids (x = mean column, y = mean row, fp64; NaN for an empty mask): the per-mask reduction of
+ * func_vpr.py:1314 `np.array(np.nonzero(m)).mean(1)[::-1]` that feeds scipy's Delaunay in nbrMasksAGGFastSingle
+ * (func_vpr.py:1309-1347; the triangulation itself stays on the host as in the reference).  centroids_xy [S, 2]. */
+int segvlad_mask_centroids(const uint8_t* masks, int S, int Hm, int Wm, double* centroids_xy, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Matching: exhaustive squared-L2 kNN of query-segment descriptors against a (shard of the)

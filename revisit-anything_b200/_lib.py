@@ -25,6 +25,7 @@ _SIGS = {
     "segvlad_aggregate_residuals": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, C.c_int, _p,
                                               C.c_size_t, _p]),
     "segvlad_mask_to_membership": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "segvlad_mask_centroids": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "segvlad_bank_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "segvlad_bank_prepare": (C.c_int, [_p, C.c_int, C.c_int, _p, _p]),
     "segvlad_bank_prepare_f64": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),

@@ -780,6 +780,39 @@ __global__ void mask_to_membership_kernel(const uint8_t* __restrict__ masks, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Mask centroids: the input of the Delaunay neighbourhood graph (func_vpr.py:1314, `np.array(np.nonzero(m)).mean(1)[::-1]`
+// = (mean column, mean row) in fp64).  The masks are on the GPU anyway (membership kernel above); the host loop over
+// np.nonzero of every 240 x 320 mask was 19 ms per image in the config-1 run, 5 x the whole aggregation.  Integer sums are
+// exact, so sum / count in fp64 is the same double numpy's mean returns (its pairwise fp64 sum of integers < 2^53 is exact
+// too); an empty mask gives 0 / 0 = NaN like numpy.  One CTA per mask.
+__global__ void __launch_bounds__(256)
+mask_centroid_kernel(const uint8_t* __restrict__ masks, int Hm, int Wm, double* __restrict__ cxy) {
+  const uint8_t* m = masks + (size_t)blockIdx.x * Hm * Wm;
+  unsigned long long sx = 0, sy = 0;
+  unsigned cnt = 0;
+  for (int i = threadIdx.x; i < Hm * Wm; i += 256) {
+    if (m[i]) { sy += (unsigned)(i / Wm); sx += (unsigned)(i % Wm); ++cnt; }
+  }
+  __shared__ unsigned long long s_x[8], s_y[8];
+  __shared__ unsigned s_c[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_xor_sync(0xffffffffu, sx, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_x[threadIdx.x >> 5] = sx; s_y[threadIdx.x >> 5] = sy; s_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long tx = 0, ty = 0;
+    unsigned tc = 0;
+    for (int w = 0; w < 8; ++w) { tx += s_x[w]; ty += s_y[w]; tc += s_c[w]; }
+    cxy[2 * blockIdx.x] = (double)tx / (double)tc;
+    cxy[2 * blockIdx.x + 1] = (double)ty / (double)tc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 struct AggLayout {
   float* chatT; float* R; float* part; float* ssq; float* nrm; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT; int* gcnt;
   int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
@@ -1009,6 +1042,15 @@ extern "C" int segvlad_mask_to_membership(const uint8_t* masks, int S, int Hm, i
   const int dh = H / patch, dw = W / patch, N = dh * dw, Wd = (N + 31) / 32;
   dim3 grid((Wd * 32 + 255) / 256, S);
   mask_to_membership_kernel<<<grid, 256, 0, st>>>(masks, S, Hm, Wm, H, W, patch, dh, dw, member_bits, Wd);
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+extern "C" int segvlad_mask_centroids(const uint8_t* masks, int S, int Hm, int Wm, double* centroids_xy, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(S >= 0 && Hm > 0 && Wm > 0 && (S == 0 || (masks && centroids_xy)), "mask_centroids: bad arguments");
+  if (S == 0) return SEGVLAD_OK;
+  mask_centroid_kernel<<<S, 256, 0, st>>>(masks, Hm, Wm, centroids_xy);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }

@@ -141,11 +141,17 @@ def getNbrsDelaunay(tri, v):
     return [[v, u] for u in indices[indptr[v]:indptr[v + 1]]]
 
 
-def nbrMasksAGGFastSingle(masks_seg, order=1):
+def nbrMasksAGGFastSingle(masks_seg, order=1, centroids=None):
+    """func_vpr.py:1309-1347.  `centroids` ([S,2] (x, y), optional): the mask centroids when the caller already has them
+    (engine.mask_centroids computes them on the GPU from the uploaded masks -- the same doubles, see the kernel); the
+    Delaunay triangulation and the adjacency power stay on the host as in the reference."""
     from scipy.spatial import Delaunay
 
     S = len(masks_seg)
-    cords = np.array([np.array(np.nonzero(m)).mean(1)[::-1] for m in masks_seg])
+    if centroids is None:
+        cords = np.array([np.array(np.nonzero(m)).mean(1)[::-1] for m in masks_seg])
+    else:
+        cords = np.asarray(centroids, dtype=np.float64).reshape(S, 2)
     adj = torch.zeros((S, S))
     if S > 3:
         tri = Delaunay(cords)

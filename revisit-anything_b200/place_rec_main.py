@@ -97,15 +97,31 @@ def build_segment_descriptors(tokens: Sequence[torch.Tensor], masks: Sequence[Se
     for b0 in range(0, len(tokens), batch_images):
         b1 = min(len(tokens), b0 + batch_images)
         tok = torch.stack([tokens[i].reshape(desc_dim, N) for i in range(b0, b1)]).to(dev, non_blocking=True)
-        counts, bits, adjs = [], [], []
-        for i in range(b0, b1):
-            ms = torch.from_numpy(np.ascontiguousarray(np.asarray(masks[i]))).to(dev)
-            bits.append(engine.mask_to_membership(ms, H, W, 14))
-            counts.append(len(masks[i]))
+        # ONE upload and one membership / centroid launch for the masks of the whole batch (same mask resolution)
+        counts = [len(masks[i]) for i in range(b0, b1)]
+        flat = [m for i in range(b0, b1) for m in masks[i]]
+        if not flat:
+            continue
+        shapes = {np.asarray(m).shape for m in flat}
+        cents = None
+        if len(shapes) == 1:
+            ms = torch.from_numpy(np.ascontiguousarray(np.stack(flat))).to(dev, non_blocking=True)
+            bits = [engine.mask_to_membership(ms, H, W, 14)]
+            if order and adjacency is None:
+                cents = engine.mask_centroids(ms).cpu().numpy()          # [S_batch, 2]: input of the host Delaunay
+        else:
+            bits = [engine.mask_to_membership(torch.from_numpy(np.ascontiguousarray(np.asarray(masks[i]))).to(dev), H, W, 14)
+                    for i in range(b0, b1) if len(masks[i])]
+        adjs, s0 = [], 0
+        for j, i in enumerate(range(b0, b1)):
             if adjacency is not None:
                 adjs.append(None if adjacency[i] is None else torch.as_tensor(adjacency[i]))
+            elif order:
+                c = None if cents is None else cents[s0:s0 + counts[j]]
+                adjs.append(func_vpr.nbrMasksAGGFastSingle(masks[i], order, centroids=c))
             else:
-                adjs.append(func_vpr.nbrMasksAGGFastSingle(masks[i], order) if order else None)
+                adjs.append(None)
+            s0 += counts[j]
             im_inds.append(np.full(len(masks[i]), i, dtype=np.int64))
         gd = engine.aggregate_batch(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
                                     adjs if order else None, out_dtype=out_dtype)

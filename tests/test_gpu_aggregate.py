@@ -249,6 +249,24 @@ def test_mask_to_membership_kernel(H, W, Hm, Wm):
                                   engine.pack_membership(torch.from_numpy(want).to(dev)).cpu().numpy())
 
 
+def test_mask_centroids_feed_the_same_adjacency():
+    # GPU centroids (integer sums / count in fp64) are the doubles of np.nonzero(m).mean (func_vpr.py:1314); the adjacency
+    # built from them equals the host-only drop-in and the oracle; an empty mask gives NaN like numpy
+    dev = torch.device("cuda")
+    for S, Hm, Wm, order in [(37, 240, 320, 3), (9, 100, 133, 2), (3, 48, 64, 1)]:
+        masks = synth.make_masks(S, Hm, Wm, 60 + S)
+        c = engine.mask_centroids(torch.from_numpy(np.stack(masks)).to(dev)).cpu().numpy()
+        want = np.array([np.array(np.nonzero(m)).mean(1)[::-1] for m in masks])
+        np.testing.assert_array_equal(c, want)
+        a_gpu = func_vpr.nbrMasksAGGFastSingle(masks, order, centroids=c)
+        assert torch.equal(a_gpu, func_vpr.nbrMasksAGGFastSingle(masks, order))
+        np.testing.assert_array_equal(a_gpu.numpy(), O.neighbour_adjacency(masks, order))
+    empty = torch.zeros((2, 8, 8), dtype=torch.uint8, device=dev)
+    empty[1, 3, 5] = 1
+    c = engine.mask_centroids(empty).cpu().numpy()
+    assert np.isnan(c[0]).all() and c[1].tolist() == [5.0, 3.0]
+
+
 def test_bad_arguments_raise():
     dev = torch.device("cuda")
     with pytest.raises(ValueError):

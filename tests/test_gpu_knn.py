@@ -136,6 +136,27 @@ def test_merge_topk_with_shards_shorter_than_k():
             assert (mi.cpu().numpy()[:, n:] == -1).all() and np.isinf(md.cpu().numpy()[:, n:]).all()
 
 
+def test_independent_third_party_brute_force_agrees():
+    # a6 is unpinned against faiss (absent offline); the oracle's flat_l2_search and the kernels come from the same hand.
+    # Two third-party exact searches break that common mode: scikit-learn's NearestNeighbors(algorithm="brute") and
+    # scipy's cdist, both on the fp32 inputs in fp64.
+    from scipy.spatial.distance import cdist
+    from sklearn.neighbors import NearestNeighbors
+    q, r = synth.make_descriptor_bank(200, 6000, 128, seed=21, planted=40, device=DEV)
+    k = 50
+    d2, idx = _run_tc(q, r, k)
+    qn, rn = q.cpu().numpy().astype(np.float64), r.cpu().numpy().astype(np.float64)
+    nn = NearestNeighbors(n_neighbors=k + 8, algorithm="brute", metric="euclidean").fit(rn)
+    dist, ind = nn.kneighbors(qn)
+    assert_knn_close(d2, idx, dist ** 2, ind.astype(np.int64), k_check=k)
+    dm = cdist(qn, rn, metric="sqeuclidean")
+    order = np.argsort(dm, axis=1, kind="stable")[:, :k + 8]
+    assert_knn_close(d2, idx, np.take_along_axis(dm, order, 1), order.astype(np.int64), k_check=k)
+    # and the oracle itself against the same third parties (CPU twin of this check: tests/test_oracle_golden.py)
+    D2o, Io = O.flat_l2_search(q.cpu().numpy(), r.cpu().numpy(), k)
+    assert_knn_close(D2o, Io, np.take_along_axis(dm, order, 1), order.astype(np.int64), k_check=k)
+
+
 def test_async_search_packed_output_and_overflow_flag():
     # segvlad_knn_async: no host synchronisation, packed (d2 bits << 32 | int32 global row) lists for the all-gather, the
     # overflow flag published on the device; identical lists to the synchronous call

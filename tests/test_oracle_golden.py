@@ -93,6 +93,32 @@ def test_flat_l2_semantics():
     assert (Is[:, 8:] == -1).all() and np.isinf(D2s[:, 8:]).all()
 
 
+def test_flat_l2_against_third_party_brute_force():
+    """a6 (faiss IndexFlatL2 is an absent, un-vendored dependency => parity unpinned against faiss itself): the oracle's
+    restatement agrees with two independent exact searches, scikit-learn's brute-force NearestNeighbors and scipy's cdist,
+    outside fp32 near-ties; its fast (timed) variant returns the same lists."""
+    from scipy.spatial.distance import cdist
+    from sklearn.neighbors import NearestNeighbors
+    rng = np.random.RandomState(5)
+    r = rng.randn(3000, 96).astype(np.float32)
+    r /= np.linalg.norm(r, axis=1, keepdims=True)
+    q = (r[rng.choice(3000, 150)] + 0.3 * rng.randn(150, 96).astype(np.float32) / 96 ** 0.5).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    k = 40
+    D2, I = O.flat_l2_search(q, r, k)
+    dist, ind = NearestNeighbors(n_neighbors=k + 1, algorithm="brute").fit(r.astype(np.float64)).kneighbors(q.astype(np.float64))
+    dm = cdist(q.astype(np.float64), r.astype(np.float64), "sqeuclidean")
+    order = np.argsort(dm, axis=1, kind="stable")[:, :k + 1]
+    for ref_d, ref_i in ((dist ** 2, ind), (np.take_along_axis(dm, order, 1), order)):
+        np.testing.assert_allclose(D2, ref_d[:, :k], rtol=1e-5, atol=2e-6)
+        gap = np.minimum(np.diff(ref_d, axis=1)[:, :k], np.concatenate([np.full((150, 1), np.inf), np.diff(ref_d, axis=1)[:, :k - 1]], 1))
+        clear = gap > 4e-6
+        assert (I[clear] == ref_i[:, :k][clear]).all() and clear.mean() > 0.95
+    D2f, If = O.flat_l2_search_fast(q, r, k)
+    np.testing.assert_allclose(D2f, D2, rtol=1e-6, atol=1e-6)
+    assert (If == I).mean() > 0.999
+
+
 def test_superseg_membership_and_empty_cluster():
     torch.manual_seed(0)
     N, D, K, S = 40, 16, 32, 4
