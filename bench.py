@@ -383,6 +383,53 @@ def pca_side_bench(device, peaks, cpu=True):
     return out
 
 
+def fused_side_bench(device, peaks):
+    """Row f1: one aggregation batch of the published configuration (16 images x 128 SuperSegments, K=32 x 1536 -> 49152,
+    PCA to 1024) through the unfused kernels (fp64 descriptors in HBM, then the projection) and through the fused path
+    (aggregation epilogue writes the projection's bf16 operand planes, projection reads them by TMA)."""
+    from revisit_anything_b200 import _lib, engine
+    lib = _lib.lib()
+    B, N, D, K, S, Dout = 16, 1530, 1536, 32, 128, 1024
+    centers, tok, member, bits = _agg_workload(device, B, N, D, K, S, seed=13)
+    counts = [S] * B
+    g = torch.Generator(device=device).manual_seed(14)
+    W = torch.randn(Dout, K * D, generator=g, device=device) / (K * D) ** 0.5
+    mu = torch.randn(K * D, generator=g, device=device, dtype=torch.float64) * 1e-3
+    ev = torch.rand(Dout, generator=g, device=device) * 1e-4 + 1e-5
+
+    def unfused():
+        x = engine.aggregate_batch(tok, N, D, 0, centers, bits, counts, None, out_dtype=torch.float64)
+        return engine.pca_project(x, W, mu, ev, normalize_rows=True)
+
+    def fused():
+        return engine.aggregate_project_pca(tok, N, D, 0, centers, bits, counts, None, W, mu, ev, normalize_rows=True)
+
+    res = {}
+    for name, fn in (("unfused", unfused), ("fused", fused)):
+        for _ in range(2):
+            y = fn()
+        torch.cuda.synchronize()
+        lib.segvlad_profile_reset()
+        lib.segvlad_profile_enable(1)
+        ms = _timed_loop(fn, 5)
+        ta, na = _prof(lib, 2)
+        tp, npc = _prof(lib, 4)
+        lib.segvlad_profile_enable(0)
+        lib.segvlad_profile_reset()
+        res[name] = {"ms_per_batch": ms, "aggregate_kernel_ms": ta / max(na, 1), "pca_kernel_ms": tp / max(npc, 1),
+                     "superseg_per_s": B * S / (ms * 1e-3)}
+        res[name + "_y"] = y
+    yu, yf = res.pop("unfused_y"), res.pop("fused_y")
+    rel = float(((yu - yf).norm(dim=1) / yu.norm(dim=1)).max())
+    inter_fp64, inter_planes = B * S * K * D * 8, B * S * K * D * 6
+    res.update({"workload": f"{B} images x {S} SuperSegments, K={K} x {D} -> {K * D}, PCA -> {Dout}, row-normalised",
+                "max_rowwise_rel_diff_fused_vs_unfused": rel,
+                "intermediate_bytes": {"unfused_fp64_write_plus_read": 2 * inter_fp64, "fused_bf16_planes_write_plus_read": 2 * inter_planes},
+                "speedup": res["unfused"]["ms_per_batch"] / res["fused"]["ms_per_batch"]})
+    del W
+    return res
+
+
 def netvlad_side_bench(device, peaks, world=1, rank=0):
     """Config 5: NetVLAD anti-burst aggregation, 128 centres x 768-D x 529 tokens; B images per rank (data parallel)."""
     from revisit_anything_b200 import engine
@@ -750,6 +797,7 @@ def main():
             out["aggregation"] = aggregation_side_bench(device, peaks, cpu)
         if "pca" in legs:
             out["pca"] = pca_side_bench(device, peaks, cpu)
+            out["aggregate_pca_fused"] = fused_side_bench(device, peaks)
         if "netvlad" in legs:
             out["netvlad"] = netvlad_side_bench(device, peaks)
         if "config1" in legs:

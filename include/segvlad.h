@@ -34,6 +34,7 @@ extern "C" {
 
 #define SEGVLAD_OUT_F64 0
 #define SEGVLAD_OUT_F32 1
+#define SEGVLAD_OUT_PCA_PLANES 2 /* segvlad_aggregate_batch_pca only: bf16 planes of (descriptor - pca mean) */
 
 #define SEGVLAD_TOKENS_DN 0 /* per image [D_t, N]  (reference h5 layout [1,D_t,dh,dw]) */
 #define SEGVLAD_TOKENS_ND 1 /* per image [N, D_t]                                      */
@@ -77,6 +78,18 @@ int segvlad_aggregate_batch(const float* tokens, int n_images, int N, int D_t, i
                             const int32_t* seg_offsets_host, const uint8_t* adj, void* out,
                             int out_dtype, int32_t* labels_out, void* workspace,
                             size_t workspace_bytes, void* stream);
+
+/* Aggregation fused with the front half of the PCA-whitening projection (place_rec_main.py:261-272 projects
+ * every aggregated batch with func_vpr.py:1419-1443): instead of the [S_total, K*D_t] fp64 descriptor matrix the kernel's
+ * epilogue writes (descriptor - pca_mean) directly as the three bf16 planes the tensor-core projection consumes,
+ * x_planes = [3][S_total][K*D_t] bf16 (plane 0 = lo, 1 = mid, 2 = hi; 6 bytes per element instead of 8, and no fp64 matrix
+ * in HBM at all).  pca_mean_f32: [K*D_t] fp32 copy of pca.mean_.  Needs D_t % 64 == 0.  Feed x_planes to
+ * segvlad_pca_project_planes.  Same workspace as segvlad_aggregate_batch. */
+int segvlad_aggregate_batch_pca(const float* tokens, int n_images, int N, int D_t, int token_layout,
+                                const float* centers, int K, const uint32_t* member_bits,
+                                const int32_t* seg_offsets_host, const uint8_t* adj, const float* pca_mean_f32,
+                                void* x_planes, int32_t* labels_out, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* Inner stage alone: aggregate caller-provided residual rows [n_images*N, D_t] fp32 with caller-provided
  * labels [n_images*N] int32.  Replaces func_vpr.py:1181-1210 vlad_matmuls_per_cluster(num_c, masks, res,
@@ -221,6 +234,13 @@ size_t segvlad_netvlad_workspace_bytes(int B, int N, int D, int K);
 int segvlad_netvlad_antiburst(const float* x, int B, int N, int D, const float* centroids,
                               const float* conv_weight, int K, float ab_w, float ab_b, float ab_p, float* out,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Back half of the fused path: Y = (x_planes . components^T) / sqrt(ev) with the A operand already split (see
+ * segvlad_aggregate_batch_pca); both operands arrive by TMA, fp32 chunk sums are folded into fp64 accumulators in TMEM as
+ * in segvlad_pca_project_tc.  Workspace: segvlad_pca_tc_workspace_bytes(S, D_in, D_out). */
+int segvlad_pca_project_planes(const void* x_planes, int S, int D_in, const void* planes, const float* explained_variance,
+                               int D_out, int normalize_rows, double* Y, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,8 @@ _SIGS = {
     "segvlad_aggregate_workspace_bytes": (C.c_size_t, [C.c_int] * 5),
     "segvlad_aggregate_batch": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p, _p, _p,
                                           C.c_int, _p, _p, C.c_size_t, _p]),
+    "segvlad_aggregate_batch_pca": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p, _p, _p, _p, _p, _p,
+                                              C.c_size_t, _p]),
     "segvlad_aggregate_residuals": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, C.c_int, _p,
                                               C.c_size_t, _p]),
     "segvlad_mask_to_membership": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
@@ -49,6 +51,7 @@ _SIGS = {
     "segvlad_pca_prepare_planes": (C.c_int, [_p, C.c_int, C.c_int, _p, _p]),
     "segvlad_pca_tc_workspace_bytes": (C.c_size_t, [C.c_int] * 3),
     "segvlad_pca_project_tc": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
+    "segvlad_pca_project_planes": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, C.c_int, C.c_int, _p, _p, C.c_size_t, _p]),
     "segvlad_netvlad_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "segvlad_netvlad_antiburst": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, C.c_float, C.c_float,
                                             C.c_float, _p, _p, C.c_size_t, _p]),

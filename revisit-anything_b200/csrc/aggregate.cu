@@ -752,6 +752,41 @@ __global__ void rownorm_fixup_kernel(const double* __restrict__ norms, const int
   for (size_t i = threadIdx.x; i < row_len; i += blockDim.x) o[i] = (OutT)((double)o[i] * f);
 }
 
+// The same correction on the PCA-planes output (SEGVLAD_OUT_PCA_PLANES): x = v - mean was split into three bf16 planes whose
+// sum is the fp32 x exactly, so v = x + mean can be rebuilt, rescaled and split again (normally no row needs it).
+__global__ void rownorm_fixup_planes_kernel(const double* __restrict__ norms, const int* __restrict__ cpred, int K, size_t row_len,
+                                            size_t plane_stride, const float* __restrict__ mean, __nv_bfloat16* __restrict__ planes) {
+  const int s = blockIdx.x;
+  __shared__ double s_factor;
+  if (threadIdx.x < 32) {
+    double tsum = 0.0;
+    for (int k = threadIdx.x; k < K; k += 32) {
+      double n = norms[(size_t)s * K + k];
+      double q = n / fmax(n, kEpsD);
+      tsum += q * q;
+    }
+    tsum = warp_sum(tsum);
+    if (threadIdx.x == 0) {
+      double m_true = sqrt(tsum), m_pred = sqrt((double)cpred[s]);
+      s_factor = (m_true == m_pred) ? 1.0 : fmax(m_pred, kEpsD) / fmax(m_true, kEpsD);
+    }
+  }
+  __syncthreads();
+  const double f = s_factor;
+  if (f == 1.0) return;
+  __nv_bfloat16* p = planes + (size_t)s * row_len;
+  for (size_t i = threadIdx.x; i < row_len; i += blockDim.x) {
+    const float x = (__bfloat162float(p[i]) + __bfloat162float(p[i + plane_stride])) + __bfloat162float(p[i + 2 * plane_stride]);
+    const float y = (float)(((double)x + (double)mean[i]) * f - (double)mean[i]);
+    const __nv_bfloat16 h = __float2bfloat16_rn(y);
+    const float r = y - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r);
+    p[i] = __float2bfloat16_rn(r - __bfloat162float(m));
+    p[i + plane_stride] = m;
+    p[i + 2 * plane_stride] = h;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pixel masks -> patch membership bits (func_vpr.py:1088-1092).  One thread per (segment, patch).
 __global__ void mask_to_membership_kernel(const uint8_t* __restrict__ masks, int S, int Hm, int Wm, int H,
@@ -865,14 +900,18 @@ extern "C" size_t segvlad_aggregate_workspace_bytes(int n_images, int N, int D_t
 static int aggregate_driver(const float* tokens, const float* residuals_in, const int32_t* labels_in, int B, int N,
                             int D, int token_layout, const float* centers, int K, const uint32_t* member_bits,
                             const int32_t* seg_offsets_host, const uint8_t* adj, void* out, int out_dtype,
-                            int32_t* labels_out, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                            int32_t* labels_out, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                            const float* pca_mean = nullptr) {
   SV_REQUIRE(B > 0 && N > 0 && D > 0 && K > 0, "aggregate: non-positive shape");
   const bool use_tc = agg_tc_supported(N, D, K);
+  SV_REQUIRE(out_dtype != SEGVLAD_OUT_PCA_PLANES || (use_tc && pca_mean && D % 64 == 0),
+             "aggregate: the PCA-planes output needs the tensor-core path (D_t %% 64 == 0) and the model mean");
   SV_REQUIRE(use_tc || (D % 4 == 0 && D <= 1536), "aggregate: D_t must be a multiple of 4 and <= 1536 (got %d)", D);
   SV_REQUIRE(K <= 128, "aggregate: K must be <= 128 (got %d)", K);
   const int layout = token_layout & 1, prenorm = (token_layout & SEGVLAD_TOKENS_PRENORMALIZED) ? 1 : 0;
   SV_REQUIRE((token_layout & ~3) == 0, "aggregate: bad token_layout");
-  SV_REQUIRE(out_dtype == SEGVLAD_OUT_F64 || out_dtype == SEGVLAD_OUT_F32, "aggregate: bad out_dtype");
+  SV_REQUIRE(out_dtype == SEGVLAD_OUT_F64 || out_dtype == SEGVLAD_OUT_F32 || out_dtype == SEGVLAD_OUT_PCA_PLANES,
+             "aggregate: bad out_dtype");
   SV_REQUIRE(seg_offsets_host && seg_offsets_host[0] == 0, "aggregate: seg_offsets_host[0] must be 0");
   const int S_total = seg_offsets_host[B];
   for (int b = 0; b < B; ++b)
@@ -968,9 +1007,13 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     ta.cl_ptr = L.cl_ptr; ta.cl_tok = L.cl_tok; ta.memS = L.memT; ta.cpred = L.cpred; ta.norms = L.norms;
     ta.seg_offsets_host = seg_offsets_host; ta.B = B; ta.N = N; ta.D = D; ta.K = K; ta.S_total = S_total;
     ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl; ta.probe = g_agg_dbg;
+    ta.pca_mean = pca_mean;
     const int rc = agg_tc_run(ta, st);
     if (rc != SEGVLAD_OK) return rc;
-    if (out_dtype == SEGVLAD_OUT_F64)
+    if (out_dtype == SEGVLAD_OUT_PCA_PLANES)
+      rownorm_fixup_planes_kernel<<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (size_t)S_total * K * D, pca_mean,
+                                                           (__nv_bfloat16*)out);
+    else if (out_dtype == SEGVLAD_OUT_F64)
       rownorm_fixup_kernel<double><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (double*)out);
     else
       rownorm_fixup_kernel<float><<<S_total, 256, 0, st>>>(L.norms, L.cpred, K, (size_t)K * D, (float*)out);
@@ -1029,6 +1072,18 @@ extern "C" int segvlad_aggregate_residuals(const float* residuals, const int32_t
   return aggregate_driver(nullptr, residuals, labels, B, N, D, SEGVLAD_TOKENS_ND, nullptr, K, member_bits,
                           seg_offsets_host, adj, out, out_dtype, nullptr, workspace, workspace_bytes,
                           reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int segvlad_aggregate_batch_pca(const float* tokens, int B, int N, int D, int token_layout, const float* centers,
+                                           int K, const uint32_t* member_bits, const int32_t* seg_offsets_host,
+                                           const uint8_t* adj, const float* pca_mean_f32, void* x_planes, int32_t* labels_out,
+                                           void* workspace, size_t workspace_bytes, void* stream_) {
+  SV_REQUIRE(tokens && centers && member_bits && x_planes && pca_mean_f32, "aggregate_batch_pca: null pointer");
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(x_planes) & 15) == 0 && (reinterpret_cast<uintptr_t>(pca_mean_f32) & 15) == 0,
+             "aggregate_batch_pca: x_planes and pca_mean_f32 must be 16-byte aligned");
+  return aggregate_driver(tokens, nullptr, nullptr, B, N, D, token_layout, centers, K, member_bits, seg_offsets_host, adj,
+                          x_planes, SEGVLAD_OUT_PCA_PLANES, labels_out, workspace, workspace_bytes,
+                          reinterpret_cast<cudaStream_t>(stream_), pca_mean_f32);
 }
 
 // timing probe: buf = device array of >= 8 * (#aggregate CTAs) uint64, or NULL to disable (not part of the product API)

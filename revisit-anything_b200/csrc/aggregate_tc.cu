@@ -28,6 +28,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 
 namespace segvlad {
@@ -292,6 +294,27 @@ template <> struct TcStage<float> {
                    : "memory");
   }
 };
+// ---- PCA-planes output (row f1): the projection's A operand, written by the aggregation itself -------------------------
+// x = v - mean split into three bf16 pieces (hi + mid + lo = all 24 mantissa bits), packed pairs.
+// all three planes of a pair in one go
+__device__ __forceinline__ void tc_plane_pair3(float x0, float x1, uint32_t& lo, uint32_t& mid, uint32_t& hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h);
+  const float r0 = x0 - hf.x, r1 = x1 - hf.y;
+  const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+  const float2 mf = __bfloat1622float2(m);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  mid = *reinterpret_cast<const uint32_t*>(&m);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+template <int kN>
+__device__ __forceinline__ void tc_plane_chunk3(const uint32_t (&v)[kN], int off, uint32_t (&o0)[4], uint32_t (&o1)[4],
+                                                uint32_t (&o2)[4]) {
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+    tc_plane_pair3(__uint_as_float(v[off + 2 * h]), __uint_as_float(v[off + 2 * h + 1]), o0[h], o1[h], o2[h]);
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int x, int y, uint64_t policy) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
                ::"l"(map), "r"(src), "r"(x), "r"(y), "l"(policy) : "memory");
@@ -300,13 +323,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 
 // kProbe: development build of the kernel with the per-role cycle counters (tools/agg_tc_probe.py); the product
 // instantiation carries none of them (they cost the epilogue registers)
-template <typename OutT, bool kProbe>
+// kPlanes (OutT = __nv_bfloat16): instead of the descriptor block the write sweep emits (block - pca_mean) split into three
+// bf16 planes, out = [3][S_total][K * D] -- the K-major A operand of the tensor-core PCA projection (project_tc.cu), which
+// then needs no converter warps and never reads an fp64 [S, K * D] matrix.
+template <typename OutT, bool kProbe, bool kPlanes>
 __global__ void __launch_bounds__(kTcThreadsAgg, 1)
 aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_constant__ CUtensorMap map_out,
                     const int* __restrict__ tile_tbl,
                     const int* __restrict__ cl_ptr, const uint16_t* __restrict__ memS, const int* __restrict__ cpred,
                     int B, int N, int D, int K, int n_items, int J, OutT* __restrict__ out, double* __restrict__ norms,
-                    unsigned long long* __restrict__ probe, int store_hint) {
+                    unsigned long long* __restrict__ probe, int store_hint, const float* __restrict__ pca_mean,
+                    int S_total) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_out = smem + kTcStages * kTcStageBytes;   // [8 epilogue warps][2 boxes][4 KB], 1024-byte aligned
@@ -504,7 +531,23 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         if (valid) {
           if (it.pj0 == 0 && half == 0) norms[(size_t)s * K + it.k] = 0.0;
           const int d_beg = it.pj0 * kTcPassN, d_end = min(D, it.pj1 * kTcPassN);
-          for (int d = d_beg + 16 * half; d < d_end; d += 32) TcOut<OutT>::zero16(orow + d);
+          if constexpr (kPlanes) {
+            // zero block: the planes hold -mean
+            const size_t KD = (size_t)K * D;
+            for (int d = d_beg + 8 * half; d < d_end; d += 16) {
+              uint32_t xv[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) xv[j] = __float_as_uint(0.f - __ldg(pca_mean + (size_t)it.k * D + d + j));
+              uint32_t o2[4], o1[4], o0[4];
+              tc_plane_chunk3(xv, 0, o0, o1, o2);
+              OutT* p0 = out + (size_t)s * KD + (size_t)it.k * D + d;
+              *reinterpret_cast<uint4*>(p0) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+              *reinterpret_cast<uint4*>(p0 + (size_t)S_total * KD) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+              *reinterpret_cast<uint4*>(p0 + 2 * (size_t)S_total * KD) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            }
+          } else {
+            for (int d = d_beg + 16 * half; d < d_end; d += 32) TcOut<OutT>::zero16(orow + d);
+          }
         }
         continue;
       }
@@ -587,7 +630,47 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        if (tma_rows && w0 == 32) {                      // (warp-uniform) all 32 rows valid, full 32-column pieces
+        if constexpr (kPlanes) {
+          // x = fl32(block * scale - mean): ONE fused multiply-add per element on the fp32 scale and the fp32 copy of the
+          // model mean (both rounded once, ~1e-7 relative of the block value; the projection's operand is fp32-equivalent
+          // anyway), kept in place of the accumulator values
+          const float scf = (float)sc;
+          const int dcol = it.k * D + pass * kTcPassN + c0;   // first of this warp's (up to) 64 columns of the [K * D] row
+          if (w0 > 0) {
+            // eight columns at a time (the compiler barrier keeps the 64 mean loads from being hoisted into 128 live registers)
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              if (g < 4 || w1 > 0) {
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(pca_mean + dcol + 8 * g));
+                const float4 m1 = __ldg(reinterpret_cast<const float4*>(pca_mean + dcol + 8 * g + 4));
+                const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (g < 4) va[8 * g + j] = __float_as_uint(fmaf(__uint_as_float(va[8 * g + j]), scf, -mm[j]));
+                  else vb[8 * (g - 4) + j] = __float_as_uint(fmaf(__uint_as_float(vb[8 * (g - 4) + j]), scf, -mm[j]));
+                }
+              }
+            }
+          }
+          const size_t KD = (size_t)K * D;
+          // Every lane writes its own row: 16-byte pieces, three planes per piece (12 registers live), 128 contiguous bytes
+          // per lane and plane -- whole sectors, no write amplification.  (Staging the three planes of a 32 x 64 box for
+          // bulk tensor stores needs either all 96 output registers at once or three staging boxes per warp: neither fits.)
+          if (valid && w0 > 0) {
+            OutT* p0 = out + (size_t)s * KD + dcol;
+            const int wtot = w0 + (w1 > 0 ? w1 : 0);       // multiple of 16 (D % 16 == 0)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              if (8 * c < wtot) {
+                uint32_t o2[4], o1[4], o0[4];
+                if (c < 4) tc_plane_chunk3(va, 8 * c, o0, o1, o2); else tc_plane_chunk3(vb, 8 * (c - 4), o0, o1, o2);
+                *reinterpret_cast<uint4*>(p0 + 8 * c) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                *reinterpret_cast<uint4*>(p0 + 8 * c + (size_t)S_total * KD) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<uint4*>(p0 + 8 * c + 2 * (size_t)S_total * KD) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+              }
+            }
+          }
+        } else if (tma_rows && w0 == 32) {                      // (warp-uniform) all 32 rows valid, full 32-column pieces
           const int xcol = it.k * D + pass * kTcPassN + c0;
           const int yrow = it.s0 + quarter * 32;
           auto flush = [&](int x) {                      // box staged by all lanes -> one bulk tensor store
@@ -601,7 +684,8 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
             __syncwarp();
             return my_stage + (nbox & 1) * kTcBoxBytes;
           };
-          if constexpr (sizeof(OutT) == 8) {
+          if constexpr (kPlanes) {
+          } else if constexpr (sizeof(OutT) == 8) {
             uint32_t sb = acquire(); TcStage<OutT>::template put<0>(sb, lane, va, sc); flush(xcol);
             sb = acquire(); TcStage<OutT>::template put<16>(sb, lane, va, sc); flush(xcol + 16);
             if (w1 == 32) {
@@ -613,8 +697,10 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
             if (w1 == 32) { sb = acquire(); TcStage<OutT>::template put<0>(sb, lane, vb, sc); flush(xcol + 32); }
           }
         } else if (valid && w0 > 0) {
-          TcOut<OutT>::store(op, va, sc, w0);
-          if (w1 > 0) TcOut<OutT>::store(op + 32, vb, sc, w1);
+          if constexpr (!kPlanes) {
+            TcOut<OutT>::store(op, va, sc, w0);
+            if (w1 > 0) TcOut<OutT>::store(op + 32, vb, sc, w1);
+          }
         }
         if (kProbe && probe) t_store += clock64() - t_s0;
         if (warp == 2 && lane == 0) TC_MARK(ti - 1, 5);
@@ -641,31 +727,34 @@ bool agg_tc_supported(int N, int D, int K) {
   return on && N >= 1 && K >= 1 && D >= 16 && D % 16 == 0 && D <= 65536;
 }
 
-template <typename OutT>
+template <typename OutT, bool kPlanes>
 static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, int J, int grid, cudaStream_t st) {
   const size_t smem = agg_tc_smem();
   // L2 evict_first policy on the output stores: the output is a pure stream and should not push the operand planes, which
   // the write sweep re-reads, out of L2 (measured: 0.441 -> 0.427 ms on the bench workload).  "0" switches it off.
   const char* se = getenv("SEGVLAD_AGG_STORE_HINT");
   const int store_hint = se ? atoi(se) : 1;
-  // output [S_total][K*D] as a 2-D tensor: the epilogue stores 32-row x 128-byte boxes through the TMA
+  // output as a 2-D tensor: the epilogue stores 32-row x 128-byte boxes through the TMA
+  //   descriptors [S_total][K*D] fp64 / fp32, or PCA planes [3 * S_total][K*D] bf16 (plane-major rows)
   CUtensorMap map_out;
   {
     PFN_encodeTiled enc = get_encode();
-    cuuint64_t dims[2] = {(cuuint64_t)a.K * a.D, (cuuint64_t)a.S_total};
+    const cuuint64_t rows = kPlanes ? (cuuint64_t)3 * a.S_total : (cuuint64_t)a.S_total;
+    cuuint64_t dims[2] = {(cuuint64_t)a.K * a.D, rows};
     cuuint64_t strides[1] = {(cuuint64_t)a.K * a.D * sizeof(OutT)};
     cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(OutT)), 32};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&map_out, sizeof(OutT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.out,
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUtensorMapDataType dt = kPlanes ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                           : (sizeof(OutT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+    CUresult r = enc(&map_out, dt, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
   }
-  auto kern = a.probe ? aggregate_tc_kernel<OutT, true> : aggregate_tc_kernel<OutT, false>;
+  auto kern = a.probe ? aggregate_tc_kernel<OutT, true, kPlanes> : aggregate_tc_kernel<OutT, false, kPlanes>;
   SV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   kern<<<grid, kTcThreadsAgg, smem, st>>>(map, map_out, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K, n_items, J,
-                                          reinterpret_cast<OutT*>(a.out), a.norms, a.probe, store_hint);
+                                          reinterpret_cast<OutT*>(a.out), a.norms, a.probe, store_hint, a.pca_mean, a.S_total);
   prof_end(pslot, st);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
@@ -726,8 +815,12 @@ int agg_tc_run(const AggTcArgs& a, cudaStream_t st) {
   const long long n_items = (long long)nt * a.K * J;
   SV_REQUIRE(n_items < (1ll << 31), "aggregate: too many work items");
   const int grid = (int)(n_items < num_sms ? n_items : num_sms);
-  return a.out_dtype == SEGVLAD_OUT_F64 ? launch_tc<double>(a, map, (int)n_items, J, grid, st)
-                                        : launch_tc<float>(a, map, (int)n_items, J, grid, st);
+  if (a.out_dtype == SEGVLAD_OUT_PCA_PLANES) {
+    SV_REQUIRE(a.pca_mean != nullptr && a.D % 64 == 0, "aggregate: the PCA-planes output needs the model mean and D_t %% 64 == 0");
+    return launch_tc<__nv_bfloat16, true>(a, map, (int)n_items, J, grid, st);
+  }
+  return a.out_dtype == SEGVLAD_OUT_F64 ? launch_tc<double, false>(a, map, (int)n_items, J, grid, st)
+                                        : launch_tc<float, false>(a, map, (int)n_items, J, grid, st);
 }
 
 }  // namespace segvlad

@@ -30,7 +30,8 @@ struct AggTcArgs {
   const int32_t* seg_offsets_host;
   int B, N, D, K, S_total;
   void* out;                  // [S_total][K*D]
-  int out_dtype;
+  int out_dtype;              // SEGVLAD_OUT_F64 / _F32, or SEGVLAD_OUT_PCA_PLANES: out = [3][S_total][K*D] bf16 planes of
+  const float* pca_mean;      // (descriptor - pca_mean) [fp32 copy of the model mean], the A operand of the tensor-core PCA projection (row f1)
   __nv_bfloat16* RT;          // workspace: [3 planes][B][D][Np] transposed, label-sorted bf16 split of R
   int* tile_tbl;              // workspace: [n_tiles][4] = image, first group, first segment, #segments
   unsigned long long* probe;  // development aid: per-CTA cycle counters [grid][16] (segvlad_debug_aggregate_probe), or null

@@ -87,8 +87,13 @@ __device__ __forceinline__ void pt_st32(uint32_t taddr, const uint32_t (&v)[32])
 }
 
 // part[z][S][Dout] (fp64) = sum over this split's channels of (X - mean) . W^T
+// kPlanesA: the A operand arrives as ready-made bf16 planes of (X - mean), [3][S][Din] (written by the aggregation kernel's
+// SEGVLAD_OUT_PCA_PLANES epilogue), through TMA like the component planes -- no converter work, no fp64 X in HBM (row f1);
+// the 16 former converter warps only fold the chunk sums into the fp64 accumulators.
+template <bool kPlanesA>
 __global__ void __launch_bounds__(kPtThreads, 1)
-pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restrict__ X, const double* __restrict__ mean,
+pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+              const double* __restrict__ X, const double* __restrict__ mean,
               int S, int Din, int Dout, int Dout_p, int stages_per_split, double* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t pt_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(pt_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -107,7 +112,7 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
   const int n_chunks = (n_st + kPtChunk - 1) / kPtChunk;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kPtStages; ++i) { mbar_init(bar_full + 8 * i, kPtConv + 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < kPtStages; ++i) { mbar_init(bar_full + 8 * i, kPlanesA ? 1 : kPtConv + 1); mbar_init(bar_empty + 8 * i, 1); }
     mbar_init(bar_tfull, 1);
     mbar_init(bar_tempty, kPtConv);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -130,9 +135,16 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
         mbar_wait(bar_empty + 8 * stage, (use & 1) ^ 1);
         const uint32_t sb = smem_u32(smem + stage * kPtStageBytes) + 3 * kPtTile;
         const uint32_t fb = bar_full + 8 * stage;
-        mbar_arrive_expect_tx(fb, 3 * kPtTile);
+        mbar_arrive_expect_tx(fb, (kPlanesA ? 6 : 3) * kPtTile);
 #pragma unroll
         for (int pl = 0; pl < 3; ++pl) tma_load_2d(sb + pl * kPtTile, &map_w, fb, (s_begin + s) * kPtCh, pl * Dout_p + n0);
+        if (kPlanesA) {
+          // rows beyond S of the last row tile read the next plane's rows (or zero fill past the end): finite garbage in
+          // accumulator rows that are never stored
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl)
+            tma_load_2d(sb - 3 * kPtTile + pl * kPtTile, &map_x, fb, (s_begin + s) * kPtCh, pl * S + row0);
+        }
       }
     }
   } else if (warp == 0) {
@@ -213,7 +225,10 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty);
     };
-    for (int s = 0; s < n_st; ++s) {
+    if (kPlanesA) {
+      for (int c = 0; c < n_chunks; ++c) drain(c);
+    }
+    for (int s = 0; !kPlanesA && s < n_st; ++s) {
       const int stage = s % kPtStages, use = s / kPtStages;
       const int d = (s_begin + s) * kPtCh + 2 * lane;      // this lane's two channels
       const bool dok = d < Din;                            // Din is even (multiple of 8)
@@ -252,7 +267,7 @@ pca_tc_kernel(const __grid_constant__ CUtensorMap map_w, const double* __restric
       if (lane == 0) mbar_arrive(bar_full + 8 * stage);
     }
     // chunks not drained inside the loop: chunk c was drained at stage 8 (c + 1) + 1 iff that stage exists
-    for (int c = 0; c < n_chunks; ++c)
+    for (int c = 0; !kPlanesA && c < n_chunks; ++c)
       if ((c + 1) * kPtChunk + 1 > n_st - 1) drain(c);
     const int r = row0 + orow;
 #pragma unroll
@@ -362,10 +377,62 @@ extern "C" int segvlad_pca_project_tc(const double* X, int S, int D_in, const vo
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (components) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
   double* part = reinterpret_cast<double*>(workspace);
   const size_t smem = pca_tc_smem();
-  SV_CHECK_CUDA(cudaFuncSetAttribute(pca_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SV_CHECK_CUDA(cudaFuncSetAttribute(pca_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(Dout_p / kPtCols, (S + kPtRows - 1) / kPtRows, z);
   const int pslot = prof_begin(SEGVLAD_PROF_PCA, st);
-  pca_tc_kernel<<<grid, kPtThreads, smem, st>>>(map, X, mean, S, D_in, D_out, Dout_p, sps, part);
+  pca_tc_kernel<false><<<grid, kPtThreads, smem, st>>>(map, map, X, mean, S, D_in, D_out, Dout_p, sps, part);
+  prof_end(pslot, st);
+  SV_CHECK_LAUNCH();
+  pca_finalize_launch(part, z, explained_variance, S, D_out, normalize_rows, Y, st);
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+extern "C" int segvlad_pca_project_planes(const void* x_planes, int S, int D_in, const void* planes, const float* explained_variance,
+                                          int D_out, int normalize_rows, double* Y, void* workspace, size_t workspace_bytes,
+                                          void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(x_planes && planes && explained_variance && Y, "pca_project_planes: null pointer");
+  SV_REQUIRE(S >= 0 && D_in >= kPtCh && D_in % 8 == 0 && D_out > 0, "pca_project_planes: unsupported shape (D_in %d, D_out %d)", D_in,
+             D_out);
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(x_planes) & 15) == 0, "pca_project_planes: x_planes must be 16-byte aligned");
+  if (S == 0) return SEGVLAD_OK;
+  const size_t need = segvlad_pca_tc_workspace_bytes(S, D_in, D_out);
+  if (!workspace || workspace_bytes < need) {
+    set_error("pca_project_planes: workspace %zu < required %zu", workspace_bytes, need);
+    return SEGVLAD_EWORKSPACE;
+  }
+  int sps = 0;
+  const int z = pca_tc_splits(S, D_in, D_out, &sps);
+  const int Dout_p = (int)align_up((size_t)D_out, kPtCols);
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SEGVLAD_ECUDA; }
+  CUtensorMap map_w, map_x;
+  cuuint32_t estr[2] = {1, 1};
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)D_in, (cuuint64_t)3 * Dout_p};
+    cuuint64_t strides[1] = {(cuuint64_t)D_in * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kPtCh, (cuuint32_t)kPtCols};
+    CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(planes), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (components) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)D_in, (cuuint64_t)3 * S};
+    cuuint64_t strides[1] = {(cuuint64_t)D_in * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kPtCh, (cuuint32_t)kPtRows};
+    CUresult r = enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x_planes), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (x planes) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
+  }
+  double* part = reinterpret_cast<double*>(workspace);
+  const size_t smem = pca_tc_smem();
+  SV_CHECK_CUDA(cudaFuncSetAttribute(pca_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(Dout_p / kPtCols, (S + kPtRows - 1) / kPtRows, z);
+  const int pslot = prof_begin(SEGVLAD_PROF_PCA, st);
+  pca_tc_kernel<true><<<grid, kPtThreads, smem, st>>>(map_w, map_x, nullptr, nullptr, S, D_in, D_out, Dout_p, sps, part);
   prof_end(pslot, st);
   SV_CHECK_LAUNCH();
   pca_finalize_launch(part, z, explained_variance, S, D_out, normalize_rows, Y, st);

@@ -118,6 +118,69 @@ def aggregate_batch(tokens: torch.Tensor, N: int, D: int, token_layout: int, cen
     return (out, labels) if return_labels else out
 
 
+def aggregate_project_pca(tokens: torch.Tensor, N: int, D: int, token_layout: int, centers: torch.Tensor,
+                          member_bits: torch.Tensor, seg_counts: Sequence[int],
+                          adj: Optional[Sequence[Optional[torch.Tensor]]], components: torch.Tensor, mean: torch.Tensor,
+                          explained_variance: torch.Tensor, normalize_rows: bool = False) -> torch.Tensor:
+    """Aggregation fused with the PCA-whitening projection: the aggregation epilogue writes
+    (descriptor - mean) as the bf16 planes the tensor-core projection consumes (segvlad_aggregate_batch_pca), the
+    projection takes both operands by TMA (segvlad_pca_project_planes).  The [S, K*D] fp64 descriptor matrix is never
+    written.  Returns Y [S_total, D_out] fp64.  Use pca_fusable() first."""
+    _need_cuda(tokens, centers, member_bits, components, mean, explained_variance)
+    B = len(seg_counts)
+    K = centers.shape[0]
+    dev = tokens.device
+    tokens = tokens.contiguous().float()
+    centers = centers.contiguous().float()
+    member_bits = member_bits.contiguous()
+    seg_off = np.zeros(B + 1, dtype=np.int32)
+    seg_off[1:] = np.cumsum(np.asarray(seg_counts, dtype=np.int64))
+    S_total = int(seg_off[-1])
+    W = components.contiguous().float()
+    Dout, Din = W.shape
+    assert Din == K * D and tokens.numel() == B * N * D and member_bits.shape == (S_total, (N + 31) // 32)
+    adj_flat = None
+    if adj is not None and any(a is not None for a in adj):
+        parts = []
+        for b in range(B):
+            Si = int(seg_counts[b])
+            a = adj[b] if adj[b] is not None else torch.eye(Si, dtype=torch.uint8, device=dev)
+            parts.append((a.to(dev) != 0).to(torch.uint8).reshape(-1))
+        adj_flat = torch.cat(parts).contiguous()
+    mean32 = _mean_f32(mean)
+    xp = torch.empty((3, S_total, Din), dtype=torch.bfloat16, device=dev)
+    ws = _ws(lib().segvlad_aggregate_workspace_bytes(B, N, D, K, S_total), dev)
+    check(lib().segvlad_aggregate_batch_pca(_ptr(tokens), B, N, D, token_layout, _ptr(centers), K, _ptr(member_bits),
+                                            seg_off.ctypes.data_as(C.c_void_p), _ptr(adj_flat), _ptr(mean32), _ptr(xp), None,
+                                            _ptr(ws), ws.numel(), _stream()), "segvlad_aggregate_batch_pca")
+    Y = torch.empty((S_total, Dout), dtype=torch.float64, device=dev)
+    ws2 = _ws(lib().segvlad_pca_tc_workspace_bytes(S_total, Din, Dout), dev)
+    check(lib().segvlad_pca_project_planes(_ptr(xp), S_total, Din, _ptr(_pca_planes(W)),
+                                           _ptr(explained_variance.contiguous().float()), Dout, int(normalize_rows), _ptr(Y),
+                                           _ptr(ws2), ws2.numel(), _stream()), "segvlad_pca_project_planes")
+    return Y
+
+
+def pca_fusable(D: int, K: int, Dout: int) -> bool:
+    """The fused aggregation -> projection path needs the tensor-core kernels of both stages (D_t % 64 == 0)."""
+    import os
+    if os.environ.get("SEGVLAD_PCA_FUSED", "1") == "0" or os.environ.get("SEGVLAD_AGG_TC", "1") == "0":
+        return False
+    return D % 64 == 0 and bool(lib().segvlad_pca_tc_supported(K * D, Dout))
+
+
+_MEAN32 = {}
+
+
+def _mean_f32(mean: torch.Tensor) -> torch.Tensor:
+    key = (mean.data_ptr(), mean.numel(), mean._version, mean.device.index)
+    ent = _MEAN32.get(key)
+    if ent is None:
+        _MEAN32.clear()
+        ent = _MEAN32[key] = (mean.to(torch.float32).contiguous(), mean)
+    return ent[0]
+
+
 def aggregate_residuals(residuals: torch.Tensor, labels: torch.Tensor, N: int, D: int, K: int,
                         member_bits: torch.Tensor, seg_counts: Sequence[int],
                         adj: Optional[Sequence[Optional[torch.Tensor]]] = None, out_dtype=torch.float64):

@@ -123,10 +123,20 @@ def build_segment_descriptors(tokens: Sequence[torch.Tensor], masks: Sequence[Se
                 adjs.append(None)
             s0 += counts[j]
             im_inds.append(np.full(len(masks[i]), i, dtype=np.int64))
-        gd = engine.aggregate_batch(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
-                                    adjs if order else None, out_dtype=out_dtype)
         if pca_model_path is not None:
-            gd = func_vpr.apply_pca_transform_from_pkl(gd, pca_model_path, device_out=True)
+            comp, mean, ev = func_vpr._load_pca(pca_model_path)
+            if engine.pca_fusable(desc_dim, centers.shape[0], comp.shape[0]):
+                # fused: the aggregation writes (descriptor - mean) as the projection's bf16 operand planes; the fp64
+                # [S, K*D] block of place_rec_main.py:259-272 never exists
+                gd = engine.aggregate_project_pca(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
+                                                  adjs if order else None, comp, mean, ev)
+            else:
+                gd = engine.aggregate_batch(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
+                                            adjs if order else None, out_dtype=out_dtype)
+                gd = func_vpr.apply_pca_transform_from_pkl(gd, pca_model_path, device_out=True)
+        else:
+            gd = engine.aggregate_batch(tok, N, desc_dim, TOKENS_DN, centers, torch.cat(bits), counts,
+                                        adjs if order else None, out_dtype=out_dtype)
         outs.append(gd)
     return torch.cat(outs), np.concatenate(im_inds)
 

@@ -87,3 +87,75 @@ def test_apply_pca_transform_from_pkl_dropin(tmp_path):
     y = func_vpr.apply_pca_transform_from_pkl(X, str(path))
     assert not y.is_cuda and y.dtype == torch.float64
     np.testing.assert_allclose(y.numpy(), pca.transform(X.numpy()), rtol=2e-5, atol=5e-8)   # sklearn 1.9: fp32 bias
+
+
+def _synthetic_pca(Din, Dout, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    qm, _ = torch.linalg.qr(torch.randn(Din, Dout, generator=g, device=dev))
+    comp = qm.T.contiguous().float()
+    mean = (torch.randn(Din, generator=g, device=dev, dtype=torch.float64) * 2e-3)
+    ev = (torch.rand(Dout, generator=g, device=dev) * 1e-4 + 1e-5).float()
+    return comp, mean, ev
+
+
+@pytest.mark.parametrize("D,K,H,W,counts,Dout,order", [(1536, 32, 480, 640, [150, 37], 1024, 3),     # published shape, 2 tiles
+                                                       (128, 64, 140, 182, [9, 1, 130], 200, 2),     # empty clusters, Dout pad
+                                                       (64, 32, 196, 266, [5], 32, 0)])
+def test_fused_aggregation_projection_matches_unfused_and_oracle(monkeypatch, D, K, H, W, counts, Dout, order):
+    """Row f1: the aggregation epilogue writes (descriptor - mean) as bf16 operand planes and the projection reads them by
+    TMA -- no [S, K*D] fp64 matrix.  Against the unfused kernels (fp64 descriptors -> tensor-core projection) and the
+    oracle (fp64 throughout)."""
+    from revisit_anything_b200 import synth
+    from revisit_anything_b200._lib import TOKENS_DN
+    dev = torch.device("cuda")
+    N = (H // 14) * (W // 14)
+    cfg = {"desired_height": H, "desired_width": W}
+    centers = synth.make_centers(K, D, 23)
+    comp, mean, ev = _synthetic_pca(K * D, Dout, 5, dev)
+    toks, bits, adjs, wants = [], [], [], []
+    for i, S in enumerate(counts):
+        t = synth.make_tokens(D, H // 14, W // 14, 640 + i, centers)
+        m = synth.make_masks(S, H // 2, W // 2, 650 + i)
+        adj = torch.from_numpy(O.neighbour_adjacency(m, order)) if order else None
+        v = O.seg_vlad_single_img(t, m, centers, cfg, adj)[0].numpy()
+        wants.append(O.pca_apply(v, mean.cpu().numpy(), comp.cpu().numpy(), ev.cpu().numpy()))
+        toks.append(t.reshape(D, N)); adjs.append(adj)
+        bits.append(engine.mask_to_membership(torch.from_numpy(np.asarray(m)).to(dev), H, W))
+    tok = torch.stack(toks).to(dev)
+    assert engine.pca_fusable(D, K, Dout)
+    fused = engine.aggregate_project_pca(tok, N, D, TOKENS_DN, centers.to(dev), torch.cat(bits), counts,
+                                         adjs if order else None, comp, mean, ev)
+    desc = engine.aggregate_batch(tok, N, D, TOKENS_DN, centers.to(dev), torch.cat(bits), counts, adjs if order else None)
+    unfused = engine.pca_project(desc, comp, mean, ev)
+    _cmp_tc(fused.cpu().numpy(), np.concatenate(wants))
+    _cmp_tc(fused.cpu().numpy(), unfused.cpu().numpy())
+    # with the row normalisation of normalizeFeat
+    fn = engine.aggregate_project_pca(tok, N, D, TOKENS_DN, centers.to(dev), torch.cat(bits), counts,
+                                      adjs if order else None, comp, mean, ev, normalize_rows=True)
+    _cmp_tc(fn.cpu().numpy(), O.normalize_feat(np.concatenate(wants)))
+
+
+def test_fused_path_zero_residual_blocks():
+    # tokens equal to their centres: populated clusters with zero block norm -> the row-norm correction must also work on
+    # the planes output (rownorm_fixup_planes_kernel)
+    from revisit_anything_b200._lib import TOKENS_ND, TOKENS_PRENORMALIZED
+    dev = torch.device("cuda")
+    D, K, N, S = 64, 32, 96, 4
+    g = torch.Generator().manual_seed(0)
+    centers = torch.nn.functional.normalize(torch.randn(K, D, generator=g), dim=1)
+    x = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=1)
+    x[:20] = centers[3]
+    x[20:30] = centers[7]
+    member = torch.rand(S, N, generator=g) < 0.4
+    member[0, :30] = True
+    member[0, 30:] = False
+    lab0, _ = O.assign_labels(x, centers)
+    member[1] = (lab0 != 3) & (torch.rand(N, generator=g) < 0.5)
+    member[1, :20] = True
+    want, _, _ = O.vlad_single(x, centers, member, None)
+    comp, mean, ev = _synthetic_pca(K * D, 48, 7, dev)
+    bits = engine.pack_membership(member.to(dev))
+    got = engine.aggregate_project_pca(x.t().contiguous().to(dev), N, D, 0 | TOKENS_PRENORMALIZED, centers.to(dev), bits, [S],
+                                       None, comp, mean, ev)
+    ref = O.pca_apply(want.numpy(), mean.cpu().numpy(), comp.cpu().numpy(), ev.cpu().numpy())
+    _cmp_tc(got.cpu().numpy(), ref)
