@@ -653,10 +653,41 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
             }
           }
           const size_t KD = (size_t)K * D;
-          // Every lane writes its own row: 16-byte pieces, three planes per piece (12 registers live), 128 contiguous bytes
-          // per lane and plane -- whole sectors, no write amplification.  (Staging the three planes of a 32 x 64 box for
-          // bulk tensor stores needs either all 96 output registers at once or three staging boxes per warp: neither fits.)
-          if (valid && w0 > 0) {
+          // Full 32-row groups go through the TMA: the three planes of a 32-row x 32-column half are staged in three
+          // SWIZZLE_64B boxes (2 KB each; row = lane, 16-byte chunk c at c ^ ((row >> 1) & 3): conflict-free) -- a chunk's
+          // three planes are computed together (12 registers live) and stored to the three boxes at once -- then three bulk
+          // tensor stores.  (r2: per-lane 16-byte global stores ran the planes epilogue at half the fp64 epilogue's rate, the
+          // L1 store path being the limit; staging one plane at a time needs the split values of all 64 columns live.)
+          if (tma_rows && w0 == 32) {
+            const int yrow = it.s0 + quarter * 32;
+#pragma unroll
+            for (int hseg = 0; hseg < 2; ++hseg) {
+              if (hseg == 0 || w1 == 32) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous boxes read out
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  uint32_t o2[4], o1[4], o0[4];
+                  if (hseg == 0) tc_plane_chunk3(va, 8 * c, o0, o1, o2); else tc_plane_chunk3(vb, 8 * c, o0, o1, o2);
+                  const uint32_t addr = my_stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0[0]), "r"(o0[1]), "r"(o0[2]), "r"(o0[3]) : "memory");
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 2048), "r"(o1[0]), "r"(o1[1]), "r"(o1[2]), "r"(o1[3]) : "memory");
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr + 4096), "r"(o2[0]), "r"(o2[1]), "r"(o2[2]), "r"(o2[3]) : "memory");
+                }
+                tc_fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                  for (int pl = 0; pl < 3; ++pl)
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                                 ::"l"(&map_out), "r"(my_stage + pl * 2048), "r"(dcol + 32 * hseg), "r"(pl * S_total + yrow),
+                                   "l"(pol_out) : "memory");
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+              }
+            }
+          } else if (valid && w0 > 0) {
+            // partial row groups / narrow tails: every lane writes its own row in 16-byte pieces
             OutT* p0 = out + (size_t)s * KD + dcol;
             const int wtot = w0 + (w1 > 0 ? w1 : 0);       // multiple of 16 (D % 16 == 0)
 #pragma unroll
@@ -742,12 +773,13 @@ static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, in
     const cuuint64_t rows = kPlanes ? (cuuint64_t)3 * a.S_total : (cuuint64_t)a.S_total;
     cuuint64_t dims[2] = {(cuuint64_t)a.K * a.D, rows};
     cuuint64_t strides[1] = {(cuuint64_t)a.K * a.D * sizeof(OutT)};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / sizeof(OutT)), 32};
+    cuuint32_t box[2] = {(cuuint32_t)(kPlanes ? 32 : 128 / sizeof(OutT)), 32};   // planes: 32 rows x 64 bytes, SWIZZLE_64B
     cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = kPlanes ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                            : (sizeof(OutT) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
-    CUresult r = enc(&map_out, dt, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(&map_out, dt, 2, a.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     kPlanes ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (output) failed (%d)", (int)r); return SEGVLAD_ECUDA; }
   }
   auto kern = a.probe ? aggregate_tc_kernel<OutT, true, kPlanes> : aggregate_tc_kernel<OutT, false, kPlanes>;
