@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsegvlad.so")
-SOURCES = ["api.cu", "aggregate.cu", "aggregate_tc.cu", "assign_tc.cu", "knn.cu", "vote.cu", "project.cu", "project_tc.cu", "netvlad.cu"]
+SOURCES = ["api.cu", "aggregate.cu", "aggregate_tc.cu", "assign_tc.cu", "knn.cu", "vote.cu", "project.cu", "project_tc.cu", "netvlad.cu", "netvlad_tc.cu"]
 HEADERS = ["common.cuh", "tc_ptx.cuh", "aggregate_tc.cuh", os.path.join("..", "..", "include", "segvlad.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -224,6 +224,16 @@ nv_finalize_kernel(const float* __restrict__ V, int D, int K, float* __restrict_
   for (int i = threadIdx.x; i < K * D; i += 1024) out[(size_t)b * K * D + i] = Vb[i] / s_nk[i / D] / tot;
 }
 
+void nv_finalize_launch(const float* V, int B, int D, int K, float* out, cudaStream_t st) {
+  nv_finalize_kernel<<<B, 1024, 0, st>>>(V, D, K, out);
+}
+
+// tensor-core path (netvlad_tc.cu)
+bool nv_tc_supported(int N, int D, int K);
+size_t nv_tc_workspace_bytes(int B, int N, int D, int K);
+int nv_tc_run(const float* x, int B, int N, int D, const float* centroids, const float* conv_weight, int K, float ab_w,
+              float ab_b, float ab_p, float* out, void* workspace, cudaStream_t st);
+
 struct NvLayout { float* xh; float* part; float* a; float* V; size_t total; };
 static NvLayout carve_nv(void* ws, int B, int N, int D, int K) {
   Carver c(ws);
@@ -243,7 +253,9 @@ using namespace segvlad;
 
 extern "C" size_t segvlad_netvlad_workspace_bytes(int B, int N, int D, int K) {
   if (B <= 0 || N <= 0 || D <= 0 || K <= 0) return 0;
-  return carve_nv(nullptr, B, N, D, K).total;
+  const size_t simt = carve_nv(nullptr, B, N, D, K).total;
+  const size_t tc = (K <= 128 && K % 16 == 0) ? nv_tc_workspace_bytes(B, N, D, K) : 0;   // (independent of the env switch)
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int segvlad_netvlad_antiburst(const float* x, int B, int N, int D, const float* centroids,
@@ -252,11 +264,14 @@ extern "C" int segvlad_netvlad_antiburst(const float* x, int B, int N, int D, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   SV_REQUIRE(x && centroids && conv_weight && out, "netvlad: null pointer");
   SV_REQUIRE(B > 0 && N > 0 && D > 0 && K > 0 && K <= 256, "netvlad: bad shape (K <= 256)");
-  NvLayout L = carve_nv(workspace, B, N, D, K);
-  if (!workspace || workspace_bytes < L.total) {
-    set_error("netvlad: workspace %zu < required %zu", workspace_bytes, L.total);
+  const size_t need = segvlad_netvlad_workspace_bytes(B, N, D, K);
+  if (!workspace || workspace_bytes < need) {
+    set_error("netvlad: workspace %zu < required %zu", workspace_bytes, need);
     return SEGVLAD_EWORKSPACE;
   }
+  if (nv_tc_supported(N, D, K))   // tcgen05: fp16 (hi, lo) split operands, three products; the FFMA kernels below stay as the
+    return nv_tc_run(x, B, N, D, centroids, conv_weight, K, ab_w, ab_b, ab_p, out, workspace, st);   // cross-check / fallback
+  NvLayout L = carve_nv(workspace, B, N, D, K);
   const int n_qt = (N + 63) / 64;
   nv_normalize_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(x, N, D, L.xh);
   SV_CHECK_LAUNCH();

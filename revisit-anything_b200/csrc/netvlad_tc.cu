@@ -450,12 +450,8 @@ int nv_tc_run(const float* x, int B, int N, int D, const float* centroids, const
   if ((rc = nv_map(&map_ap, AP, Np, (uint64_t)2 * B * kNvTile, kNvTile))) return rc;
   if ((rc = nv_map(&map_xt, XT, Np, (uint64_t)2 * B * Dp, kNvTile))) return rc;
   const size_t smem = nv_tc_smem();
-  static thread_local bool attrs = false;
-  if (!attrs) {
-    SV_CHECK_CUDA(cudaFuncSetAttribute(nv_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SV_CHECK_CUDA(cudaFuncSetAttribute(nv_vlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attrs = true;
-  }
+  SV_CHECK_CUDA(cudaFuncSetAttribute(nv_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SV_CHECK_CUDA(cudaFuncSetAttribute(nv_vlad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   nv_assign_tc_kernel<<<dim3(Np / kNvTile, B), kNvThreads, smem, st>>>(map_xh, map_w, B, N, Np, Dp, K, Kp, ab_w, ab_b, ab_p, AP,
                                                                       asum_part);
   SV_CHECK_LAUNCH();

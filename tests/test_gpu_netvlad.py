@@ -31,3 +31,30 @@ def test_netvlad_antiburst_vs_oracle(B, D, H, K, ab):
     assert got.shape == (B, K * D)
     np.testing.assert_allclose(got.norm(dim=1).cpu().numpy(), 1.0, atol=1e-5)
     assert_desc_close(got.cpu().numpy(), want.numpy(), rtol=2e-5)   # fp32 on both sides (reference: fp32 / fp16 autocast)
+
+
+def test_tensor_core_path_matches_ffma_path_and_is_deterministic(monkeypatch):
+    # tcgen05 kernels (fp16 hi/lo split operands, csrc/netvlad_tc.cu) against the fp32 FFMA kernels (SEGVLAD_NETVLAD_TC=0), on a
+    # bursty image (a quarter of the tokens are copies of one token) and a K that is not 128; two runs are bit-identical
+    g = torch.Generator().manual_seed(77)
+    B, D, H, K = 3, 768, 23, 64
+    x = torch.randn(B, D, H, H, generator=g)
+    x[1, :, :6, :] = x[1, :, :1, :1]
+    cent, W = _params(K, D, 5)
+    xc, cc, wc = x.cuda(), cent.cuda(), W.cuda()
+    a = engine.netvlad_antiburst(xc, cc, wc)
+    b = engine.netvlad_antiburst(xc, cc, wc)
+    assert torch.equal(a, b)
+    monkeypatch.setenv("SEGVLAD_NETVLAD_TC", "0")
+    c = engine.netvlad_antiburst(xc, cc, wc)
+    assert_desc_close(a.cpu().numpy(), c.cpu().numpy(), rtol=2e-5)
+    want = O.netvlad_antiburst(x.reshape(B, D, -1), cent, W)
+    assert_desc_close(a.cpu().numpy(), want.numpy(), rtol=2e-5)
+
+
+def test_unsupported_cluster_count_uses_the_ffma_kernels():
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 6, 6, generator=g)
+    cent, W = _params(24, 64, 9)                                # K = 24: not a multiple of 16
+    got = engine.netvlad_antiburst(x.cuda(), cent.cuda(), W.cuda())
+    assert_desc_close(got.cpu().numpy(), O.netvlad_antiburst(x.reshape(2, 64, -1), cent, W).numpy(), rtol=2e-5)
