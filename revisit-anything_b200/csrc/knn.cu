@@ -686,7 +686,8 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
     vor = __reduce_or_sync(0xffffffffu, vor);
     vand = __reduce_and_sync(0xffffffffu, vand);
     if (lane == 0) { s_or[w] = vor; s_and[w] = vand; }
-    __syncthreads();
+    if (tid == 0) s_out = 0;   // (here, not next to its first use: s_bin / s_kk / s_out / s_val share one 16-byte word that the
+    __syncthreads();           //  digit loop reads with a vector load -- racecheck flagged the later single-thread write)
     vor = 0u; vand = 0xffffffffu;
 #pragma unroll
     for (int ww = 0; ww < 8; ++ww) { vor |= s_or[ww]; vand &= s_and[ww]; }
@@ -730,8 +731,6 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
     if (compact) T = prefix;
     // approximate scores: everything within 2E of the k-th best may still belong to the exact top k
     const unsigned keepT = mode == kRefineSelect ? __float_as_uint(__fadd_ru(__uint_as_float(T), twoE)) : T;
-    if (tid == 0) s_out = 0;
-    __syncthreads();
     for (int i0 = 0; compact && i0 < n; i0 += 256) {
       const int i = i0 + tid;
       const unsigned v = i < n ? s_v[i] : 0xffffffffu;

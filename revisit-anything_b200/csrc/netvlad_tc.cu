@@ -42,48 +42,65 @@ __device__ __forceinline__ void nv_split_store(float v, __half* hi, __half* lo) 
 // tokens [B][D][N] -> unit-norm x_hat split into fp16 (hi, lo) planes in both operand layouts, zero padded.
 //   XH [2][B][Np][Dp]  row = token (K-major for contractions over the channels)
 //   XT [2][B][Dp][Np]  row = channel (K-major for the contraction over the tokens)
+// CTA = (image, 32 tokens): the whole [D][32] fp32 slab is staged in shared memory (D x 33 floats, 101 KB at D = 768), so x
+// is read from HBM ONCE for both the norms and the planes (r2 launch lists: 2-byte stores 1.06 ms per 512 images; 64-token
+// CTAs with 4-byte stores but a second pass over x 1.24 ms -- with ~1200 CTAs' slabs in flight the second read misses L2),
+// and written out in both orientations with 4-byte (half2) stores.
+__device__ __forceinline__ void nv_split2(float v0, float v1, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(hi);
+  lo = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+}
+constexpr int kNvPrepTok = 32;
 __global__ void __launch_bounds__(256)
 nv_prep_kernel(const float* __restrict__ x, int B, int N, int D, int Np, int Dp, __half* __restrict__ XH,
                __half* __restrict__ XT) {
-  const int b = blockIdx.y, p0 = blockIdx.x * 32;
+  extern __shared__ float s_slab[];             // [Dp][33]: channel-major slab of this CTA's 32 tokens (zero padded)
+  __shared__ float s_part[8][32];
+  __shared__ float s_nrm[32];
+  const int b = blockIdx.y, p0 = blockIdx.x * kNvPrepTok;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* xb = x + (size_t)b * D * N;
   const int p = p0 + lane;
   const bool ok = p < N;
-  const float* xb = x + (size_t)b * D * N;
-  __shared__ float s_ss[8][32];
-  __shared__ float s_t[8][32][33];
   float ss = 0.f;
-  for (int d = w; d < D; d += 8) {
-    const float v = ok ? xb[(size_t)d * N + p] : 0.f;
+  for (int d = w; d < Dp; d += 8) {             // warp w: channels w, w + 8, ...; lane = token: 128-byte row pieces
+    const float v = (d < D && ok) ? __ldg(xb + (size_t)d * N + p) : 0.f;
+    s_slab[d * 33 + lane] = v;
     ss = fmaf(v, v, ss);
   }
-  s_ss[w][lane] = ss;
+  s_part[w][lane] = ss;
   __syncthreads();
-  float tot = 0.f;
+  if (w == 0) {
+    float t = 0.f;
 #pragma unroll
-  for (int ww = 0; ww < 8; ++ww) tot += s_ss[ww][lane];
-  const float nrm = fmaxf(sqrtf(tot), 1e-12f);
+    for (int ww = 0; ww < 8; ++ww) t += s_part[ww][lane];
+    s_nrm[lane] = fmaxf(sqrtf(t), 1e-12f);      // max(||x_p||, eps) like F.normalize
+  }
+  __syncthreads();
   const size_t plane_h = (size_t)B * Np * Dp, plane_t = (size_t)B * Dp * Np;
-  const int dchunk = (Dp / 8 + 31) / 32 * 32;           // channels per warp (multiple of 32)
-  const int d0 = w * dchunk, d1 = min(Dp, d0 + dchunk);
-  for (int dd = d0; dd < d1; dd += 32) {
-    for (int r = 0; r < 32; ++r) {
-      const int d = dd + r;
-      const float v = (d < D && ok) ? xb[(size_t)d * N + p] / nrm : 0.f;
-      s_t[w][r][lane] = v;
-      if (d < d1) {                                      // channel-major: 32 consecutive tokens per row piece
-        const size_t o = ((size_t)b * Dp + d) * Np + p;
-        nv_split_store(v, XT + o, XT + plane_t + o);
-      }
+  // channel-major planes: a warp writes two channel rows per step (half-warp = one row of 16 token pairs = 64 bytes)
+  {
+    const int hw = lane >> 4, l = lane & 15;
+    const float n0 = s_nrm[2 * l], n1 = s_nrm[2 * l + 1];
+    for (int d = 2 * w + hw; d < Dp; d += 16) {
+      __half2 hi, lo;
+      nv_split2(s_slab[d * 33 + 2 * l] / n0, s_slab[d * 33 + 2 * l + 1] / n1, hi, lo);
+      const size_t o = ((size_t)b * Dp + d) * Np + p0 + 2 * l;
+      *reinterpret_cast<__half2*>(XT + o) = hi;
+      *reinterpret_cast<__half2*>(XT + plane_t + o) = lo;
     }
-    __syncwarp();
-    const int d = dd + lane;
-    if (d < d1)
-      for (int t = 0; t < 32; ++t) {                     // token-major: 32 consecutive channels per row piece
-        const size_t o = ((size_t)b * Np + p0 + t) * Dp + d;
-        nv_split_store(s_t[w][lane][t], XH + o, XH + plane_h + o);
-      }
-    __syncwarp();
+  }
+  // token-major planes: warp w writes tokens w, w + 8, ...; lane = channel pair, 128 contiguous bytes per store
+  for (int t = w; t < kNvPrepTok; t += 8) {
+    const float nt = s_nrm[t];
+    const size_t row = ((size_t)b * Np + p0 + t) * Dp;
+    for (int d = 2 * lane; d < Dp; d += 64) {
+      __half2 hi, lo;
+      nv_split2(s_slab[d * 33 + t] / nt, s_slab[(d + 1) * 33 + t] / nt, hi, lo);
+      *reinterpret_cast<__half2*>(XH + row + d) = hi;
+      *reinterpret_cast<__half2*>(XH + plane_h + row + d) = lo;
+    }
   }
 }
 
@@ -361,6 +378,7 @@ nv_vlad_tc_kernel(const __grid_constant__ CUtensorMap map_ap, const __grid_const
     // epilogue: thread = cluster row
     const int quarter = warp & 3;
     const int k = quarter * 32 + lane;
+    const bool vec4 = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(V) | reinterpret_cast<uintptr_t>(cent)) & 15) == 0;
     float asum = 0.f;
     if (k < K)
       for (int i = 0; i < Np / 32; ++i) asum += asum_part[((size_t)b * (Np / 32) + i) * kNvTile + k];   // fixed order
@@ -375,9 +393,22 @@ nv_vlad_tc_kernel(const __grid_constant__ CUtensorMap map_ap, const __grid_const
       if (k < K) {
         float* o = V + ((size_t)b * K + k) * D + d0 + c;
         const float* cr = cent + (size_t)k * D + d0 + c;
+        if (vec4 && d0 + c + 16 <= D) {          // 64 contiguous bytes per thread: whole sectors, 16-byte accesses
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (d0 + c + j < D) o[j] = (__uint_as_float(vm[j]) + __uint_as_float(vs[j])) - cr[j] * asum;
+          for (int j = 0; j < 16; j += 4) {
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(cr + j));
+            float4 r;
+            r.x = (__uint_as_float(vm[j]) + __uint_as_float(vs[j])) - cv.x * asum;
+            r.y = (__uint_as_float(vm[j + 1]) + __uint_as_float(vs[j + 1])) - cv.y * asum;
+            r.z = (__uint_as_float(vm[j + 2]) + __uint_as_float(vs[j + 2])) - cv.z * asum;
+            r.w = (__uint_as_float(vm[j + 3]) + __uint_as_float(vs[j + 3])) - cv.w * asum;
+            *reinterpret_cast<float4*>(o + j) = r;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (d0 + c + j < D) o[j] = (__uint_as_float(vm[j]) + __uint_as_float(vs[j])) - cr[j] * asum;
+        }
       }
     }
   }
@@ -393,7 +424,7 @@ nv_vlad_tc_kernel(const __grid_constant__ CUtensorMap map_ap, const __grid_const
 bool nv_tc_supported(int N, int D, int K) {
   const char* e = getenv("SEGVLAD_NETVLAD_TC");   // "0" selects the fp32 FFMA kernels of netvlad.cu (kept as the cross-check)
   const bool on = !(e && e[0] == '0');
-  return on && N >= 1 && D >= 8 && K >= 16 && K <= 128 && K % 16 == 0;
+  return on && N >= 1 && D >= 8 && D <= 1536 && K >= 16 && K <= 128 && K % 16 == 0;   // D: shared-memory slab of nv_prep_kernel
 }
 static inline int nv_np(int N) { return (int)align_up((size_t)N, kNvTile); }
 static inline int nv_dp(int D) { return (int)align_up((size_t)D, kNvTile); }   // 128: also the channel tile of the V kernel
@@ -439,7 +470,10 @@ int nv_tc_run(const float* x, int B, int N, int D, const float* centroids, const
   float* V = c.take<float>((size_t)B * K * D);
   // cluster rows K .. 127 of AP are never written by the assignment kernel: the V kernel's A tile must read zeros there
   if (K < kNvTile) SV_CHECK_CUDA(cudaMemsetAsync(AP, 0, sizeof(__half) * (size_t)2 * B * kNvTile * Np, st));
-  nv_prep_kernel<<<dim3(Np / 32, B), 256, 0, st>>>(x, B, N, D, Np, Dp, XH, XT);
+  const size_t psmem = (size_t)Dp * 33 * sizeof(float);
+  SV_REQUIRE(psmem <= 200 * 1024, "netvlad: D too large for the tensor-core path");
+  SV_CHECK_CUDA(cudaFuncSetAttribute(nv_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+  nv_prep_kernel<<<dim3(Np / kNvPrepTok, B), 256, psmem, st>>>(x, B, N, D, Np, Dp, XH, XT);
   SV_CHECK_LAUNCH();
   nv_wplanes_kernel<<<64, 256, 0, st>>>(conv_weight, K, D, Kp, Dp, WP);
   SV_CHECK_LAUNCH();

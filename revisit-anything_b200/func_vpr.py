@@ -320,10 +320,10 @@ def _open_store(desc_path):
     if isinstance(desc_path, (str, bytes)):
         try:
             import h5py
-        except ImportError as e:
-            raise RuntimeError("segvlad: h5py is not installed; pass an opened mapping {img: {'ift_dino': array}} or "
-                               "convert the file with revisit_anything_b200.store") from e
-        return h5py.File(desc_path, "r")
+            return h5py.File(desc_path, "r")
+        except ImportError:
+            from . import h5min          # pure-Python reader of the HDF5 subset the reference's files use (f3)
+            return h5min.File(desc_path, "r")
     return desc_path
 
 
