@@ -293,7 +293,7 @@ template <> struct TcCfg<2> { static constexpr int kStagesT = 6; static constexp
 constexpr uint32_t kQTileBytes = kTileM * kTileK * 2;   // 16 KB
 template <int kCtas> __host__ __device__ constexpr uint32_t tc_stage_bytes() { return (kTileM + TcCfg<kCtas>::kRRows) * kTileK * 2; }
 template <int kCtas> __host__ __device__ constexpr size_t tc_smem_bytes() {
-  return TcCfg<kCtas>::kStagesT * tc_stage_bytes<kCtas>() + 1024 /*align*/ + 256 /*barriers*/;
+  return TcCfg<kCtas>::kStagesT * tc_stage_bytes<kCtas>() + 1024 /*align*/ + 256 /*barriers*/ + 4096 /*column constants*/;
 }
 
 constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address (-> even CTA)
@@ -347,6 +347,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSt * kStageB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* cc_inv = reinterpret_cast<float*>(bars + 32);   // [2 tile parities][kTileN] 2^(e_r - 14) of the tile's columns
+  float* cc_nrn = cc_inv + 2 * kTileN;                   // [2][kTileN] -||r||^2
   const uint32_t bar_full = smem_u32(bars + 0);        // [kSt <= 8]  (pairs: only the leader's copies are used)
   const uint32_t bar_empty = smem_u32(bars + 8);       // [kSt <= 8]
   const uint32_t bar_tfull = smem_u32(bars + 16);      // [2] accumulator ready
@@ -499,25 +501,36 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         int* ci = sel.cand_idx + (size_t)row * kCandCap;
         // test: u = (acc * 2 inv_q) * inv_r - ||r||^2 >= thr; u replaces the accumulator value in v[] because the
         // survivor's approximate d2 is simply ||q||^2 - u (no second look-up of the column constants)
+        // The tile's 256 column constants are staged in shared memory once per tile by the 256 epilogue threads (one column
+        // each; double-buffered by tile parity, one named barrier per tile) and read back as broadcast 8-byte pairs; the
+        // test runs on packed fp32 pairs (mul.f32x2 / fma.f32x2: the same roundings as the scalar form, bit-identical u).
+        // r2 ncu at D = 512: with a broadcast LDG.128 per column and scalar FMUL / FFMA the epilogue (~6 us per tile) was
+        // twice the tile's MMA time and the tensor pipe 35-38 % active.
+        {
+          const int e = (warp - 2) * 32 + lane;
+          const int gcol = min(c0 + ct * kTileN + e, c1 - 1);
+          const float4 rmc = __ldg(rmeta + gcol);
+          cc_inv[(it & 1) * kTileN + e] = rmc.y;
+          cc_nrn[(it & 1) * kTileN + e] = -rmc.x;
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+        }
+        const float2* tinv = reinterpret_cast<const float2*>(cc_inv + (it & 1) * kTileN + half * (kTileN / 2));
+        const float2* tnrn = reinterpret_cast<const float2*>(cc_nrn + (it & 1) * kTileN + half * (kTileN / 2));
+        const float2 cq2 = make_float2(cq, cq);
         auto test_chunk = [&](uint32_t (&v)[32], int col0) -> uint32_t {
           uint32_t m = 0;
-          if (col0 + 32 <= c1) {
+          const int lc = (col0 - colbase) >> 1;              // pair index inside this warp's half of the tile
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4 rm = __ldg(rmeta + col0 + j);
-              const float u = fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x);
-              v[j] = __float_as_uint(u);
-              if (u >= thr) m |= 1u << j;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4 rm = __ldg(rmeta + min(col0 + j, c1 - 1));
-              const float u = fmaf(__uint_as_float(v[j]) * cq, rm.y, -rm.x);
-              v[j] = __float_as_uint(u);
-              if (col0 + j < c1 && u >= thr) m |= 1u << j;
-            }
+          for (int j = 0; j < 32; j += 2) {
+            const float2 a = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            const float2 u = __ffma2_rn(__fmul2_rn(a, cq2), tinv[lc + (j >> 1)], tnrn[lc + (j >> 1)]);
+            v[j] = __float_as_uint(u.x);
+            v[j + 1] = __float_as_uint(u.y);
+            if (u.x >= thr) m |= 1u << j;
+            if (u.y >= thr) m |= 2u << j;
           }
+          const int nv = c1 - col0;                          // columns of this chunk inside the scanned range
+          if (nv < 32) m = nv <= 0 ? 0u : (m & ((1u << nv) - 1u));
           return m;
         };
         auto store_chunk = [&](const uint32_t (&v)[32], uint32_t m, int pos, int col0) {

@@ -63,10 +63,19 @@ nv_prep_kernel(const float* __restrict__ x, int B, int N, int D, int Np, int Dp,
   const float* xb = x + (size_t)b * D * N;
   const int p = p0 + lane;
   const bool ok = p < N;
+  // warp w: channels w, w + 8, ...; lane = token: 128-byte row pieces.  All of a thread's 4-byte copies are issued as
+  // cp.async before anything waits (r2: the first version's register loads kept ~8 KB in flight per SM and ran the kernel at
+  // 2.5 TB/s); padding tokens / channels are zero-filled by a copy of source size 0.
+  for (int d = w; d < Dp; d += 8) {
+    const bool in = d < D && ok;
+    const float* src = in ? xb + (size_t)d * N + p : xb;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(s_slab + d * 33 + lane)), "l"(src),
+                 "r"(in ? 4 : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   float ss = 0.f;
-  for (int d = w; d < Dp; d += 8) {             // warp w: channels w, w + 8, ...; lane = token: 128-byte row pieces
-    const float v = (d < D && ok) ? __ldg(xb + (size_t)d * N + p) : 0.f;
-    s_slab[d * 33 + lane] = v;
+  for (int d = w; d < Dp; d += 8) {             // (each thread reads back exactly what it copied: no barrier needed yet)
+    const float v = s_slab[d * 33 + lane];
     ss = fmaf(v, v, ss);
   }
   s_part[w][lane] = ss;
