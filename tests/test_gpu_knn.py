@@ -211,7 +211,8 @@ def test_merge_packed_is_the_same_k_way_merge():
     r[10] = r[400]
     k = 200
     qb = engine.Bank.prepare(q)
-    for bounds in ([0, 60, 150, 700], [0, 50, 120, 180], [0, 350, 700]):
+    for bounds in ([0, 60, 150, 700], [0, 50, 120, 180], [0, 350, 700], [0, 90, 170, 260, 350, 430, 520, 610, 700],
+                   [0, 10, 20, 30, 40, 50, 60, 70, 700]):        # 8 shards: balanced, and one shard holding almost everything
         n, G = bounds[-1], len(bounds) - 1
         d2_full, idx_full = engine.knn(qb, engine.Bank.prepare(r[:n]), k)
         buf = torch.zeros((G, 130 * k + Dm.TRAILER), dtype=torch.int64, device=DEV)
