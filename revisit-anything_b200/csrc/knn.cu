@@ -461,6 +461,16 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         thr = qnr - (sel.tau[row] + 2.f * row_err_bound(em, q_row0 + row));
       }
       const int colbase = c0 + ct * kTileN + half * (kTileN / 2);
+      if (!first_round) {
+        // this tile's column constants -> shared memory, BEFORE waiting for the accumulator (the loads and the barrier of
+        // the 8 epilogue warps overlap the tile's MMAs; buffers alternate with the tile parity)
+        const int e = (warp - 2) * 32 + lane;
+        const int gcol = min(c0 + ct * kTileN + e, c1 - 1);
+        const float4 rmc = __ldg(rmeta + gcol);
+        cc_inv[(it & 1) * kTileN + e] = rmc.y;
+        cc_nrn[(it & 1) * kTileN + e] = -rmc.x;
+        asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+      }
       mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN + half * (kTileN / 2);
@@ -506,14 +516,6 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // test runs on packed fp32 pairs (mul.f32x2 / fma.f32x2: the same roundings as the scalar form, bit-identical u).
         // r2 ncu at D = 512: with a broadcast LDG.128 per column and scalar FMUL / FFMA the epilogue (~6 us per tile) was
         // twice the tile's MMA time and the tensor pipe 35-38 % active.
-        {
-          const int e = (warp - 2) * 32 + lane;
-          const int gcol = min(c0 + ct * kTileN + e, c1 - 1);
-          const float4 rmc = __ldg(rmeta + gcol);
-          cc_inv[(it & 1) * kTileN + e] = rmc.y;
-          cc_nrn[(it & 1) * kTileN + e] = -rmc.x;
-          asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
-        }
         const float2* tinv = reinterpret_cast<const float2*>(cc_inv + (it & 1) * kTileN + half * (kTileN / 2));
         const float2* tnrn = reinterpret_cast<const float2*>(cc_nrn + (it & 1) * kTileN + half * (kTileN / 2));
         const float2 cq2 = make_float2(cq, cq);

@@ -87,14 +87,20 @@ nv_prep_kernel(const float* __restrict__ x, int B, int N, int D, int Np, int Dp,
     s_nrm[lane] = fmaxf(sqrtf(t), 1e-12f);      // max(||x_p||, eps) like F.normalize
   }
   __syncthreads();
+  // normalise the slab in place: ONE fp32 division per element (x / max(||x||, eps) like F.normalize), by the thread that
+  // copied it (r2 ncu: with the division inside both write-out loops the kernel was issue-bound at 58 %)
+  {
+    const float nl = s_nrm[lane];
+    for (int d = w; d < Dp; d += 8) s_slab[d * 33 + lane] = s_slab[d * 33 + lane] / nl;
+  }
+  __syncthreads();
   const size_t plane_h = (size_t)B * Np * Dp, plane_t = (size_t)B * Dp * Np;
   // channel-major planes: a warp writes two channel rows per step (half-warp = one row of 16 token pairs = 64 bytes)
   {
     const int hw = lane >> 4, l = lane & 15;
-    const float n0 = s_nrm[2 * l], n1 = s_nrm[2 * l + 1];
     for (int d = 2 * w + hw; d < Dp; d += 16) {
       __half2 hi, lo;
-      nv_split2(s_slab[d * 33 + 2 * l] / n0, s_slab[d * 33 + 2 * l + 1] / n1, hi, lo);
+      nv_split2(s_slab[d * 33 + 2 * l], s_slab[d * 33 + 2 * l + 1], hi, lo);
       const size_t o = ((size_t)b * Dp + d) * Np + p0 + 2 * l;
       *reinterpret_cast<__half2*>(XT + o) = hi;
       *reinterpret_cast<__half2*>(XT + plane_t + o) = lo;
@@ -102,11 +108,10 @@ nv_prep_kernel(const float* __restrict__ x, int B, int N, int D, int Np, int Dp,
   }
   // token-major planes: warp w writes tokens w, w + 8, ...; lane = channel pair, 128 contiguous bytes per store
   for (int t = w; t < kNvPrepTok; t += 8) {
-    const float nt = s_nrm[t];
     const size_t row = ((size_t)b * Np + p0 + t) * Dp;
     for (int d = 2 * lane; d < Dp; d += 64) {
       __half2 hi, lo;
-      nv_split2(s_slab[d * 33 + t] / nt, s_slab[(d + 1) * 33 + t] / nt, hi, lo);
+      nv_split2(s_slab[d * 33 + t], s_slab[(d + 1) * 33 + t], hi, lo);
       *reinterpret_cast<__half2*>(XH + row + d) = hi;
       *reinterpret_cast<__half2*>(XH + plane_h + row + d) = lo;
     }

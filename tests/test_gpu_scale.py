@@ -76,3 +76,22 @@ def test_rescore_by_reference_row_is_bit_identical_to_the_gather(monkeypatch):
         rows = torch.arange(0, Nq, 97, device=DEV)
         d64, i64 = _brute_fp64(q[rows], r, 208)
         assert_knn_close(d2a[rows].cpu().numpy(), ia[rows].cpu().numpy(), d64, i64, k_check=200)
+
+
+def test_inverted_rescore_falls_back_to_the_gather_when_the_pair_lists_do_not_fit():
+    # 3000 exact copies of one row sit at the k-th-neighbour boundary of every query: ~3000 candidates per query survive the
+    # select (> the 512 pairs per query row the inverted lists hold) -> the device-side flag leaves the re-score to the
+    # gather kernel; the result must still be the exact (d2, idx)-ordered top-k: duplicates in index order
+    Nq, Nr, D, k = 400, 20000, 256, 200
+    q, r = synth.make_descriptor_bank(Nq, Nr, D, seed=47, planted=0, device=DEV)
+    centre = torch.nn.functional.normalize(q.mean(0), dim=0)
+    q = torch.nn.functional.normalize(q * 0.2 + centre, dim=1)          # all queries close to one direction
+    dup_rows = torch.arange(5000, 8000, device=DEV)
+    r[dup_rows] = centre                                                 # the 3000 nearest references of every query, all equal
+    d2, idx = engine.knn(engine.Bank.prepare(q), engine.Bank.prepare(r), k)
+    torch.cuda.synchronize()
+    assert torch.equal(idx, dup_rows[:k].expand(Nq, k))                  # ties broken by index
+    want = ((q - centre) ** 2).sum(1, keepdim=True).expand(Nq, k)
+    np.testing.assert_allclose(d2.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    d2s, idxs = engine.knn_simt(q, r, k)
+    assert torch.equal(idx, idxs)
