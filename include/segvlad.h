@@ -119,6 +119,10 @@ int segvlad_mask_centroids(const uint8_t* masks, int S, int Hm, int Wm, double* 
  */
 size_t segvlad_bank_bytes(int n, int D);
 int segvlad_bank_prepare(const float* x, int n, int D, void* bank, void* stream);
+/* Same, but the bank REFERENCES the caller's fp32 rows instead of copying them (the exact re-score reads x directly): x must
+ * stay valid and unchanged for as long as the bank is searched.  Saves the 4 n D byte copy of every index.add
+ * (place_rec_main.py:55, 59 re-adds the whole reference set on every recall_segloc call).  x 16-byte aligned. */
+int segvlad_bank_prepare_view(const float* x, int n, int D, void* bank, void* stream);
 /* fp64 input (the reference keeps segFtVLAD1/2 in fp64): optional row L2-normalise in fp64 WITHOUT eps
  * (func_vpr.py:1673-1676 normalizeFeat, place_rec_main.py:55-56), then the fp32 cast faiss's Python
  * wrapper performs, then the split. */

@@ -30,6 +30,7 @@ _SIGS = {
     "segvlad_mask_centroids": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "segvlad_bank_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "segvlad_bank_prepare": (C.c_int, [_p, C.c_int, C.c_int, _p, _p]),
+    "segvlad_bank_prepare_view": (C.c_int, [_p, C.c_int, C.c_int, _p, _p]),
     "segvlad_bank_prepare_f64": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "segvlad_knn_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "segvlad_knn": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int64, C.c_int, C.c_int, _p, _p, _p, C.c_size_t, _p]),

@@ -79,8 +79,9 @@ struct BankView {
   const float* norms;     // [n] ||x||^2 (fp32)
   const float4* meta;     // [n] {||x||^2, 2^(e_row - 14), rho = ||x - h16 / scale||_2 (rounded up), ||x|| (rounded up)}
   const unsigned* stats;  // [0] max rho, [1] max ||x|| over the prepared rows (bit patterns of non-negative floats)
-  const float* x32;       // [n][D] fp32 rows: exact re-scoring of the selected candidates
-  int Dp;
+  const float* x32;       // [n][D] fp32 rows inside the bank (exact re-scoring of the selected candidates) -- or unused when
+  const float* const* x32_slot;   // the bank is a VIEW: *x32_slot (device word in the stats block) is where the rows live:
+  int Dp;                 // the bank's own region or the caller's matrix (segvlad_bank_prepare_view: no 4 n D byte copy)
 };
 static inline int padded_dim(int D) { return (int)align_up((size_t)D, kTileK); }
 static BankView bank_view(const void* bank, int n, int D) {
@@ -92,6 +93,7 @@ static BankView bank_view(const void* bank, int n, int D) {
   v.meta = c.take<float4>(n);
   v.stats = c.take<unsigned>(64);
   v.x32 = c.take<float>((size_t)n * D);
+  v.x32_slot = reinterpret_cast<const float* const*>(v.stats + 8);
   return v;
 }
 struct BankOut { __half* h16; float* norms; float4* meta; unsigned* stats; float* x32; int Dp; };
@@ -141,7 +143,8 @@ __device__ __forceinline__ void bank_finish_row(const BankOut& b, int row, int D
   }
 }
 
-__global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, BankOut b) {
+// copy_rows = 0: b.x32 IS x (view bank): nothing to copy, the second half reads the caller's rows
+__global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, BankOut b, int copy_rows) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -150,7 +153,7 @@ __global__ void bank_prepare_kernel(const float* __restrict__ x, int n, int D, B
   float ss = 0.f, mx = 0.f;
   for (int d = lane; d < D; d += 32) {
     const float v = xr[d];
-    x32r[d] = v;
+    if (copy_rows) x32r[d] = v;
     ss = fmaf(v, v, ss);
     mx = fmaxf(mx, fabsf(v));
   }
@@ -821,10 +824,12 @@ knn_refine_kernel(SelState sel, ErrModel em, int k, int mode, int dense_first, l
 // persistent CTAs (2.1-2.8 ms vs 1.8 ms: the gather is bound by memory-level parallelism, which one CTA per query
 // row with every warp on its own candidate maximises), two candidates per warp iteration (register pressure).
 __global__ void __launch_bounds__(256)
-knn_rescore_kernel(SelState sel, const float* __restrict__ q32, const float* __restrict__ r32,
+knn_rescore_kernel(SelState sel, const float* const* __restrict__ q32_slot, const float* const* __restrict__ r32_slot,
                    const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int D,
                    const int* __restrict__ done_flag) {
   if (done_flag && *done_flag) return;   // the inverted pass (knn_rescore_ref_kernel) re-scored everything
+  const float* __restrict__ q32 = *q32_slot;   // fp32 rows: the bank's own copy or the caller's matrix (view banks)
+  const float* __restrict__ r32 = *r32_slot;
   const int row = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   int n = sel.cnt[row];
   if (n > kCandCap) n = kCandCap;
@@ -958,10 +963,13 @@ inv_scatter_kernel(SelState sel, InvState inv) {
 // grid-stride over reference rows, one warp per row; after the scatter ref_off[r] is the END of row r's pair list and
 // ref_off[r - 1] its start.  Shared memory: kRefWarps rows of D floats.
 __global__ void __launch_bounds__(kRefWarps * 32)
-knn_rescore_ref_kernel(SelState sel, InvState inv, const float* __restrict__ q32, const float* __restrict__ r32,
-                       const float* __restrict__ qn, const float* __restrict__ rn, int q_row0, int Nr, int D) {
+knn_rescore_ref_kernel(SelState sel, InvState inv, const float* const* __restrict__ q32_slot,
+                       const float* const* __restrict__ r32_slot, const float* __restrict__ qn, const float* __restrict__ rn,
+                       int q_row0, int Nr, int D) {
   extern __shared__ __align__(16) float s_ref[];
   if (inv.state[1] == 0) return;
+  const float* __restrict__ q32 = *q32_slot;
+  const float* __restrict__ r32 = *r32_slot;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* my = s_ref + (size_t)w * D;
   const bool vec = (D & 3) == 0;
@@ -1390,11 +1398,11 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         int rgrid = ta->num_sms * ctas_per_sm;
         if (rgrid > (Nr + kRefWarps - 1) / kRefWarps) rgrid = (Nr + kRefWarps - 1) / kRefWarps;
-        knn_rescore_ref_kernel<<<rgrid, kRefWarps * 32, rsmem, st>>>(L.sel, L.inv, ta->q.x32, ta->r.x32, ta->q.norms,
+        knn_rescore_ref_kernel<<<rgrid, kRefWarps * 32, rsmem, st>>>(L.sel, L.inv, ta->q.x32_slot, ta->r.x32_slot, ta->q.norms,
                                                                     ta->r.norms, q_row0, Nr, D);
         SV_CHECK_LAUNCH();
       }
-      knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32, ta->r.x32, ta->q.norms, ta->r.norms, q_row0, D,
+      knn_rescore_kernel<<<rows, 256, 0, st>>>(L.sel, ta->q.x32_slot, ta->r.x32_slot, ta->q.norms, ta->r.norms, q_row0, D,
                                                by_ref ? L.inv.state + 1 : nullptr);
       prof_end(rslot, st);
       SV_CHECK_LAUNCH();
@@ -1500,6 +1508,11 @@ static int knn_driver(bool tc, TcArgs* ta, const SimtArgs* sa, int Nq, int Nr, i
   return SEGVLAD_OK;
 }
 
+// where the fp32 rows of a bank live: device word [stats + 8] (written on the stream, after the stats block was cleared)
+static cudaError_t set_rows_slot(const BankOut& b, const float* rows, cudaStream_t st) {
+  return cudaMemcpyAsync(b.stats + 8, &rows, sizeof(rows), cudaMemcpyHostToDevice, st);   // pageable source: staged at once
+}
+
 }  // namespace segvlad
 
 using namespace segvlad;
@@ -1523,7 +1536,23 @@ extern "C" int segvlad_bank_prepare(const float* x, int n, int D, void* bank, vo
   if (n == 0) return SEGVLAD_OK;
   BankOut b = bank_out(bank_view(bank, n, D));
   SV_CHECK_CUDA(cudaMemsetAsync(b.stats, 0, 64 * sizeof(unsigned), st));
-  bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, b);
+  SV_CHECK_CUDA(set_rows_slot(b, b.x32, st));
+  bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, b, 1);
+  SV_CHECK_LAUNCH();
+  return SEGVLAD_OK;
+}
+
+extern "C" int segvlad_bank_prepare_view(const float* x, int n, int D, void* bank, void* stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  SV_REQUIRE(n >= 0 && D > 0 && bank && (x || n == 0), "bank_prepare_view: bad arguments");
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(bank) & 255) == 0, "bank_prepare_view: bank must be 256-byte aligned");
+  SV_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 || (D & 3) != 0, "bank_prepare_view: x must be 16-byte aligned");
+  if (n == 0) return SEGVLAD_OK;
+  BankOut b = bank_out(bank_view(bank, n, D));
+  SV_CHECK_CUDA(cudaMemsetAsync(b.stats, 0, 64 * sizeof(unsigned), st));
+  SV_CHECK_CUDA(set_rows_slot(b, x, st));
+  b.x32 = const_cast<float*>(x);          // the split reads the caller's rows; nothing is copied
+  bank_prepare_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, b, 0);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }
@@ -1535,6 +1564,7 @@ extern "C" int segvlad_bank_prepare_f64(const double* x, int n, int D, int norma
   if (n == 0) return SEGVLAD_OK;
   BankOut b = bank_out(bank_view(bank, n, D));
   SV_CHECK_CUDA(cudaMemsetAsync(b.stats, 0, 64 * sizeof(unsigned), st));
+  SV_CHECK_CUDA(set_rows_slot(b, b.x32, st));
   bank_prepare_f64_kernel<<<(n + 7) / 8, 256, 0, st>>>(x, n, D, normalize_rows, b);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
@@ -1639,6 +1669,8 @@ extern "C" int segvlad_knn_from_host(const float* q_host, int Nq, const float* r
   SV_CHECK_CUDA(cudaStreamWaitEvent(st, eq, 0));
   SV_CHECK_CUDA(cudaMemsetAsync(const_cast<unsigned*>(ta.q.stats), 0, 64 * sizeof(unsigned), st));
   SV_CHECK_CUDA(cudaMemsetAsync(const_cast<unsigned*>(ta.r.stats), 0, 64 * sizeof(unsigned), st));
+  SV_CHECK_CUDA(set_rows_slot(bank_out(ta.q), ta.q.x32, st));
+  SV_CHECK_CUDA(set_rows_slot(bank_out(ta.r), ta.r.x32, st));
   bank_prepare_rows_kernel<<<(Nq + 7) / 8, 256, 0, st>>>(0, Nq, D, bank_out(ta.q));
   SV_CHECK_LAUNCH();
   // copy / scan sub-chunks of 8192 rows; banks beyond ~3 M rows use proportionally larger ones (<= ~400 sub-chunks)

@@ -221,15 +221,21 @@ class Bank:
     buf: torch.Tensor
     n: int
     D: int
+    src: Optional[torch.Tensor] = None     # view banks: the fp32 matrix the bank references (kept alive here)
 
     @staticmethod
-    def prepare(x: torch.Tensor) -> "Bank":
+    def prepare(x: torch.Tensor, copy: bool = False) -> "Bank":
+        """fp32 [n, D] CUDA matrix -> bank.  By default the bank REFERENCES x for the exact re-score (no 4 n D byte copy;
+        do not modify x while the bank is in use); copy=True stores its own copy of the rows."""
         _need_cuda(x)
         x = x.contiguous().float()
         n, D = x.shape
         buf = _ws(lib().segvlad_bank_bytes(n, D), x.device)
-        check(lib().segvlad_bank_prepare(_ptr(x), n, D, _ptr(buf), _stream()), "segvlad_bank_prepare")
-        return Bank(buf, n, D)
+        if copy or x.data_ptr() % 16 != 0:
+            check(lib().segvlad_bank_prepare(_ptr(x), n, D, _ptr(buf), _stream()), "segvlad_bank_prepare")
+            return Bank(buf, n, D)
+        check(lib().segvlad_bank_prepare_view(_ptr(x), n, D, _ptr(buf), _stream()), "segvlad_bank_prepare_view")
+        return Bank(buf, n, D, x)
 
     @staticmethod
     def prepare_f64(x: torch.Tensor, normalize_rows: bool = False) -> "Bank":

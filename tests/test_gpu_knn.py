@@ -157,6 +157,23 @@ def test_independent_third_party_brute_force_agrees():
     assert_knn_close(D2o, Io, np.take_along_axis(dm, order, 1), order.astype(np.int64), k_check=k)
 
 
+def test_view_bank_equals_copy_bank():
+    # Bank.prepare references the caller's fp32 rows by default (segvlad_bank_prepare_view); copy=True owns them: same lists,
+    # also through the row-offset / sliced-shard path (a row slice of a contiguous matrix is itself contiguous and aligned)
+    q, r = synth.make_descriptor_bank(500, 30000, 512, seed=31, planted=60, device=DEV)
+    qv, rv = engine.Bank.prepare(q), engine.Bank.prepare(r)
+    qc, rc = engine.Bank.prepare(q, copy=True), engine.Bank.prepare(r, copy=True)
+    assert rv.src is not None and rc.src is None
+    a = engine.knn(qv, rv, 200)
+    b = engine.knn(qc, rc, 200)
+    c = engine.knn(qv, rc, 200)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    s = engine.knn(qv, engine.Bank.prepare(r[10000:]), 200, row_offset=10000)
+    d64, i64 = _ref(q, r[10000:], 208)
+    assert_knn_close(s[0].cpu().numpy(), s[1].cpu().numpy() - 10000, d64, i64, k_check=200)
+
+
 def test_async_search_packed_output_and_overflow_flag():
     # segvlad_knn_async: no host synchronisation, packed (d2 bits << 32 | int32 global row) lists for the all-gather, the
     # overflow flag published on the device; identical lists to the synchronous call
