@@ -47,6 +47,8 @@ constexpr int kExactFlag = (int)0x80000000;  // cand_idx sign bit: this candidat
 constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
 constexpr int kTcThreads = 320;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quarter)
+constexpr int kTcThreadsWide = 576; // ... or 16 epilogue warps (4 per lane quarter, 64 columns each): shallow contractions
+                                    // (D <= 1024), where a tile's MMAs are too short to hide an 8-warp epilogue
 
 struct SelState {
   float* tau;      // [rows] current k-th best d2 (+inf until k candidates seen)
@@ -335,8 +337,10 @@ __device__ __forceinline__ float make_d2_scaled(float qn, float rn, float acc, f
   return v > 0.f ? v : 0.f;
 }
 
-template <int kCtas>
-__global__ void __launch_bounds__(kTcThreads, 1)
+// kEpi: epilogue warps per CTA (8 or 16).  r2 ncu at D = 512: a 256 x 256 tile's MMAs take ~2.1 us, the 8-warp epilogue
+// (128 columns per thread, latency-bound at ~1 instruction per clock and SM) ~5.6 us -> tensor pipe 35-38 %.
+template <int kCtas, int kEpi>
+__global__ void __launch_bounds__(64 + 32 * kEpi, 1)
 knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_r,
                      const float4* __restrict__ rmeta, ErrModel em, int q_row0, int rows, int c0, int c1, int num_kb,
                      int first_round, SelState sel) {
@@ -368,7 +372,7 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSt; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 8 * kCtas); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, kEpi * kCtas); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: all 512 columns = two 128x256 fp32 accumulators (per CTA)
@@ -447,8 +451,10 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // Survivor slots are claimed with ONE atomic per (row, 32-column chunk); the atomic's round trip is hidden behind
     // the next chunk's TMEM load and tests, then the chunk's survivors are stored column by column, skipping (warp-
     // uniformly) the columns in which no lane has one.
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
-    constexpr int kChunksPerWarp = kTileN / 32 / 2;
+    constexpr int kParts = kEpi / 4;                 // column parts of a tile (one warp per part and TMEM lane quarter)
+    constexpr int kPartCols = kTileN / kParts;       // 128 or 64 columns per warp
+    const int quarter = warp & 3, half = (warp - 2) >> 2;    // `half`: this warp's column part (0 .. kParts - 1)
+    constexpr int kChunksPerWarp = kPartCols / 32;
     uint32_t it = 0;
     for (int t = worker; t < n_tiles; t += n_workers, ++it) {
       const int ct = t / n_row_tiles, rt = t - ct * n_row_tiles;
@@ -463,24 +469,26 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // keep approx <= T + 2E (header comment); tau = +inf -> thr = -inf
         thr = qnr - (sel.tau[row] + 2.f * row_err_bound(em, q_row0 + row));
       }
-      const int colbase = c0 + ct * kTileN + half * (kTileN / 2);
+      const int colbase = c0 + ct * kTileN + half * kPartCols;
       if (!first_round) {
         // this tile's column constants -> shared memory, BEFORE waiting for the accumulator (the loads and the barrier of
         // the 8 epilogue warps overlap the tile's MMAs; buffers alternate with the tile parity)
         const int e = (warp - 2) * 32 + lane;
-        const int gcol = min(c0 + ct * kTileN + e, c1 - 1);
-        const float4 rmc = __ldg(rmeta + gcol);
-        cc_inv[(it & 1) * kTileN + e] = rmc.y;
-        cc_nrn[(it & 1) * kTileN + e] = -rmc.x;
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+        if (e < kTileN) {
+          const int gcol = min(c0 + ct * kTileN + e, c1 - 1);
+          const float4 rmc = __ldg(rmeta + gcol);
+          cc_inv[(it & 1) * kTileN + e] = rmc.y;
+          cc_nrn[(it & 1) * kTileN + e] = -rmc.x;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpi) : "memory");     // the epilogue warps
       }
       mbar_wait(bar_tfull + 8 * buf, use & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN + half * (kTileN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * kTileN + half * kPartCols;
       if (first_round) {
         // round 0: tau = +inf, every score is a candidate -> dense store at (col - c0), no counters
 #pragma unroll 1
-        for (int c = 0; c < kTileN / 2; c += 32) {
+        for (int c = 0; c < kPartCols; c += 32) {
           uint32_t v[32];
           tc_ld32(taddr + c, v);
           if (row_ok) {
@@ -519,8 +527,8 @@ knn_tc_filter_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         // test runs on packed fp32 pairs (mul.f32x2 / fma.f32x2: the same roundings as the scalar form, bit-identical u).
         // r2 ncu at D = 512: with a broadcast LDG.128 per column and scalar FMUL / FFMA the epilogue (~6 us per tile) was
         // twice the tile's MMA time and the tensor pipe 35-38 % active.
-        const float2* tinv = reinterpret_cast<const float2*>(cc_inv + (it & 1) * kTileN + half * (kTileN / 2));
-        const float2* tnrn = reinterpret_cast<const float2*>(cc_nrn + (it & 1) * kTileN + half * (kTileN / 2));
+        const float2* tinv = reinterpret_cast<const float2*>(cc_inv + (it & 1) * kTileN + half * kPartCols);
+        const float2* tnrn = reinterpret_cast<const float2*>(cc_nrn + (it & 1) * kTileN + half * kPartCols);
         const float2 cq2 = make_float2(cq, cq);
         auto test_chunk = [&](uint32_t (&v)[32], int col0) -> uint32_t {
           uint32_t m = 0;
@@ -1253,7 +1261,7 @@ static int dev_ctx(DevCtx** out) {
 }
 constexpr int kEvFork = 0, kEvJoin0 = 1, kEvJoin1 = 2, kEvHost0 = 3, kEvHostQ = 4, kEvFeed = 8;   // event pool slots
 
-struct TcArgs { BankView q, r; CUtensorMap mq, mr; int num_sms; int ctas; };
+struct TcArgs { BankView q, r; CUtensorMap mq, mr; int num_sms; int ctas; int epi; };
 struct KnnOut { float* d2; long long* idx; unsigned long long* packed; };   // final lists: unpacked and / or packed
 // asynchronous mode (segvlad_knn_async): no host synchronisation -- the chosen schedule runs, the OR of the query blocks'
 // overflow flags goes to overflow_dev and the caller decides (after ITS synchronisation point) whether to repeat the
@@ -1270,6 +1278,36 @@ struct HostFeed {
   int sub_rows;            // rows per copy / scan sub-chunk (multiple of kTileN)
 };
 struct SubChunk { int c0, c1; int first_round; int last_of_round; int final_pass; };
+
+// one launch of the tcgen05 filter kernel over reference columns [c0, c1) for `rows` queries starting at q_row0
+template <int kCtas, int kEpi>
+static int launch_filter_t(const TcArgs* ta, const ErrModel& em, int q_row0, int rows, int c0, int c1, int first_round,
+                           const SelState& sel, cudaStream_t st) {
+  const int chunk = c1 - c0;
+  const int n_tiles = ((rows + kCtas * kTileM - 1) / (kCtas * kTileM)) * ((chunk + kTileN - 1) / kTileN);
+  int workers = ta->num_sms / kCtas;
+  if (n_tiles < workers) workers = n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kCtas * workers);
+  cfg.blockDim = dim3(64 + 32 * kEpi);
+  cfg.dynamicSmemBytes = tc_smem_bytes<kCtas>();
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = kCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<kCtas, kEpi>, ta->mq, ta->mr, ta->r.meta, em, q_row0, rows, c0, c1,
+                                   ta->q.Dp / kTileK, first_round, sel));
+  return SEGVLAD_OK;
+}
+static int launch_filter(const TcArgs* ta, const ErrModel& em, int q_row0, int rows, int c0, int c1, int first_round,
+                         const SelState& sel, cudaStream_t st) {
+  if (ta->ctas == 2)
+    return ta->epi == 16 ? launch_filter_t<2, 16>(ta, em, q_row0, rows, c0, c1, first_round, sel, st)
+                         : launch_filter_t<2, 8>(ta, em, q_row0, rows, c0, c1, first_round, sel, st);
+  return ta->epi == 16 ? launch_filter_t<1, 16>(ta, em, q_row0, rows, c0, c1, first_round, sel, st)
+                       : launch_filter_t<1, 8>(ta, em, q_row0, rows, c0, c1, first_round, sel, st);
+}
 
 struct BlockCtx { SelState sel; InvState inv; const float* qn; const float* rn; };
 
@@ -1333,27 +1371,8 @@ static int run_block(bool tc, const TcArgs* ta, const SimtArgs* sa, const BlockC
     }
     const int pslot = prof_begin(SEGVLAD_PROF_KNN_FILTER, st);
     if (tc) {
-      if (ta->ctas == 2) {
-        const int n_tiles = ((rows + 2 * kTileM - 1) / (2 * kTileM)) * ((chunk + kTileN - 1) / kTileN);
-        int pairs = ta->num_sms / 2;
-        if (n_tiles < pairs) pairs = n_tiles;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(kTcThreads);
-        cfg.dynamicSmemBytes = tc_smem_bytes<2>();
-        cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<2>, ta->mq, ta->mr, ta->r.meta, em, q_row0, rows, c0,
-                                         c1, ta->q.Dp / kTileK, first_round, L.sel));
-      } else {
-        const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((chunk + kTileN - 1) / kTileN);
-        const int grid = n_tiles < ta->num_sms ? n_tiles : ta->num_sms;
-        knn_tc_filter_kernel<1><<<grid, kTcThreads, tc_smem_bytes<1>(), st>>>(
-            ta->mq, ta->mr, ta->r.meta, em, q_row0, rows, c0, c1, ta->q.Dp / kTileK, first_round, L.sel);
-      }
+      const int frc = launch_filter(ta, em, q_row0, rows, c0, c1, first_round, L.sel, st);
+      if (frc) return frc;
     } else {
       dim3 grid((chunk + 63) / 64, (rows + 63) / 64);
       knn_simt_filter_kernel<<<grid, 256, 0, st>>>(sa->q + (size_t)q_row0 * D, sa->r, L.qn + q_row0, L.rn, rows, D, c0,
@@ -1582,6 +1601,9 @@ static int tc_setup(TcArgs& ta, const void* qbank, int Nq, const void* rbank, in
   int rc;
   const char* env = getenv("SEGVLAD_KNN_CTAS");      // 2 (default): CTA pairs / cta_group::2; 1: single-CTA tiles
   ta.ctas = (env && env[0] == '1') ? 1 : 2;
+  // epilogue warps: 16 for shallow contractions (D <= 1024: the tile's MMAs are too short to hide 8 warps), else 8
+  const char* ee = getenv("SEGVLAD_KNN_EPI");
+  ta.epi = ee ? (atoi(ee) == 16 ? 16 : 8) : (padded_dim(D) <= 1024 ? 16 : 8);
   const int r_box = ta.ctas == 2 ? kTileN / 2 : kTileN;
   if ((rc = make_map(&ta.mq, ta.q.h16, Nq, ta.q.Dp, kTileM))) return rc;
   if ((rc = make_map(&ta.mr, ta.r.h16, Nr, ta.r.Dp, r_box))) return rc;
@@ -1589,9 +1611,13 @@ static int tc_setup(TcArgs& ta, const void* qbank, int Nq, const void* rbank, in
   if ((rc = dev_ctx(&dc))) return rc;
   ta.num_sms = dc->num_sms;
   if (!dc->attrs_set) {   // once per (thread, device)
-    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc_smem_bytes<1>()));
-    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes<2>()));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc_smem_bytes<1>()));
+    SV_CHECK_CUDA(cudaFuncSetAttribute(knn_tc_filter_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)tc_smem_bytes<2>()));
     SV_CHECK_CUDA(cudaFuncSetAttribute(knn_rescore_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kRefWarps * kRefMaxD * (int)sizeof(float)));
@@ -1698,27 +1724,7 @@ extern "C" int segvlad_knn_debug_approx(const void* qbank, int Nq, const void* r
     const int rows = (Nq - q0) < L.block_rows ? (Nq - q0) : L.block_rows;
     sel_init_kernel<<<(rows + 255) / 256, 256, 0, st>>>(L.sel[0], rows, Nr);
     SV_CHECK_LAUNCH();
-    if (ta.ctas == 2) {
-      const int n_tiles = ((rows + 2 * kTileM - 1) / (2 * kTileM)) * ((Nr + kTileN - 1) / kTileN);
-      int pairs = ta.num_sms / 2;
-      if (n_tiles < pairs) pairs = n_tiles;
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(2 * pairs);
-      cfg.blockDim = dim3(kTcThreads);
-      cfg.dynamicSmemBytes = tc_smem_bytes<2>();
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      SV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, knn_tc_filter_kernel<2>, ta.mq, ta.mr, ta.r.meta, em, q0, rows, 0, Nr,
-                                       ta.q.Dp / kTileK, 1, L.sel[0]));
-    } else {
-      const int n_tiles = ((rows + kTileM - 1) / kTileM) * ((Nr + kTileN - 1) / kTileN);
-      const int grid = n_tiles < ta.num_sms ? n_tiles : ta.num_sms;
-      knn_tc_filter_kernel<1><<<grid, kTcThreads, tc_smem_bytes<1>(), st>>>(ta.mq, ta.mr, ta.r.meta, em, q0, rows, 0, Nr,
-                                                                          ta.q.Dp / kTileK, 1, L.sel[0]);
-    }
+    { const int frc = launch_filter(&ta, em, q0, rows, 0, Nr, 1, L.sel[0], st); if (frc) return frc; }
     SV_CHECK_LAUNCH();
     knn_debug_copy_kernel<<<rows, 256, 0, st>>>(L.sel[0], em, q0, rows, Nr, approx_out, bound_out);
     SV_CHECK_LAUNCH();

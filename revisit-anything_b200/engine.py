@@ -371,9 +371,6 @@ class VoteResult:
     minmax: torch.Tensor           # [2] fp32
 
 
-_MAX_SEGS = {}   # (offsets ptr, numel, version, device) -> largest number of segments of one query image
-
-
 def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, rseg_to_rimg: torch.Tensor,
          n_rimg: int, n_pred: int = 5, k_vote: int = 50, sims_is_d2: bool = False, dense: bool = False,
          max_segs: Optional[int] = None, qrow_index: Optional[torch.Tensor] = None) -> VoteResult:
@@ -387,6 +384,7 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
     Nq, ld = matches.shape[0], matches.stride(0) if matches.shape[0] > 1 else matches.shape[1]
     k_vote = min(k_vote, matches.shape[1])
     dev = matches.device
+    offsets_in = qimg_offsets
     if max_segs is None and not qimg_offsets.is_cuda and qimg_offsets.numel() > 1:
         max_segs = int((qimg_offsets[1:] - qimg_offsets[:-1]).max())      # host offsets: no device read at all
     qimg_offsets = qimg_offsets.to(device=dev, dtype=torch.int32).contiguous()
@@ -395,15 +393,18 @@ def vote(matches: torch.Tensor, sims: torch.Tensor, qimg_offsets: torch.Tensor, 
     if qrow_index is not None:
         qrow_index = qrow_index.to(device=dev, dtype=torch.int32).contiguous()
     if max_segs is None:
-        # a device -> host read; cached per offsets tensor so that a pipeline voting repeatedly with the same query-image
-        # layout (every bench step, every shard merge) synchronises for it once, not before every vote
-        key = (qimg_offsets.data_ptr(), qimg_offsets.numel(), qimg_offsets._version, dev.index)
-        max_segs = _MAX_SEGS.get(key)
-        if max_segs is None:
+        # a device -> host read; remembered ON the offsets tensor object (with its version counter), so that a pipeline voting
+        # repeatedly with the same query-image layout (every bench step, every shard merge) synchronises for it once, not
+        # before every vote -- and a different tensor can never pick up a stale value
+        memo = getattr(offsets_in, "_segvlad_max_segs", None)
+        if memo is not None and memo[0] == offsets_in._version:
+            max_segs = memo[1]
+        else:
             max_segs = int((qimg_offsets[1:] - qimg_offsets[:-1]).max().item()) if n_qimg > 0 else 0
-            if len(_MAX_SEGS) > 64:
-                _MAX_SEGS.clear()
-            _MAX_SEGS[key] = max_segs
+            try:
+                offsets_in._segvlad_max_segs = (offsets_in._version, max_segs)
+            except AttributeError:
+                pass
     preds = torch.empty((n_qimg, n_pred), dtype=torch.int32, device=dev)
     pscores = torch.empty((n_qimg, n_pred), dtype=torch.float64, device=dev)
     scores = torch.empty((n_qimg, n_rimg), dtype=torch.float64, device=dev) if dense else None

@@ -95,3 +95,18 @@ def test_inverted_rescore_falls_back_to_the_gather_when_the_pair_lists_do_not_fi
     np.testing.assert_allclose(d2.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=2e-6)
     d2s, idxs = engine.knn_simt(q, r, k)
     assert torch.equal(idx, idxs)
+
+
+@pytest.mark.parametrize("D,force", [(512, "8"), (1536, "16"), (96, "8")])
+def test_epilogue_width_variants_agree(monkeypatch, D, force):
+    # 8 or 16 epilogue warps in the scan kernel (default: 16 for D <= 1024, else 8; csrc/knn.cu kEpi): the candidate sets may
+    # be stored in a different order, the exact re-score + (d2, idx) selection makes the output identical
+    q, r = synth.make_descriptor_bank(2000, 40000, D, seed=48, planted=200, device=DEV)
+    qb, rb = engine.Bank.prepare(q), engine.Bank.prepare(r)
+    d2a, ia = engine.knn(qb, rb, 200)
+    monkeypatch.setenv("SEGVLAD_KNN_EPI", force)
+    d2b, ib = engine.knn(qb, rb, 200)
+    monkeypatch.setenv("SEGVLAD_KNN_CTAS", "1")
+    d2c, ic = engine.knn(qb, rb, 200)
+    torch.cuda.synchronize()
+    assert torch.equal(d2a, d2b) and torch.equal(ia, ib) and torch.equal(d2a, d2c) and torch.equal(ia, ic)
