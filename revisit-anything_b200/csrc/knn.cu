@@ -612,14 +612,16 @@ constexpr int kLooseBin = 32;
 constexpr int kSmallSort = 512;   // up to this many candidates: sort them all, no selection passes
 
 __device__ __forceinline__ void bitonic_sort_keys(unsigned long long* keys, int P, int tid) {
+  // every compare-exchange is owned by one thread: t enumerates the P / 2 pairs of a stage, i = t with a zero bit inserted at
+  // the stage's distance j (r2: looping over all P indices and skipping the upper partner wasted half the iterations of an
+  // issue-bound kernel)
   for (int kk2 = 2; kk2 <= P; kk2 <<= 1) {
     for (int j = kk2 >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += 256) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          if ((a > b) == ((i & kk2) == 0)) { keys[i] = b; keys[ixj] = a; }
-        }
+      for (int t = tid; t < (P >> 1); t += 256) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i | j;
+        const unsigned long long a = keys[i], b = keys[ixj];
+        if ((a > b) == ((i & kk2) == 0)) { keys[i] = b; keys[ixj] = a; }
       }
       __syncthreads();
     }

@@ -96,16 +96,15 @@ vote_kernel(const long long* __restrict__ matches, const float* __restrict__ sim
     hc[t] = 0;
   }
   __syncthreads();
-  // bitonic sort, ascending
+  // bitonic sort, ascending; t enumerates the P / 2 compare-exchanges of a stage (i = t with a zero bit inserted at distance j)
   for (int k = 2; k <= P; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += kVoteThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
-        }
+      for (int t = tid; t < (P >> 1); t += kVoteThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int ixj = i | j;
+        const unsigned long long a = keys[i], b = keys[ixj];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
       }
       __syncthreads();
     }
