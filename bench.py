@@ -742,9 +742,21 @@ def main():
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        # the same host -> device bytes with no compute at all: the PCIe floor of this box for the e2e step
+        qd, rd = torch.empty_like(q_dev), torch.empty_like(r_dev)
+
+        def h2d_only():
+            qd.copy_(q_host, non_blocking=True)
+            rd.copy_(r_host, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        h2d_only()
+        ms_h2d = timed(h2d_only, 3) / 3
+        del qd, rd
         e2e = {"value": pairs_step / (ms_e2e / args.steps * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e / args.steps,
                "h2d_bytes_per_step": int(q_host.numel() * 4 + r_host.numel() * 4),
-               "d2h_bytes_per_step": int(preds_host.numel() * 4)}
+               "d2h_bytes_per_step": int(preds_host.numel() * 4),
+               "h2d_only_ms": ms_h2d, "h2d_only_note": "the step's host->device copies alone (pinned, no compute): PCIe floor"}
         del q_host, r_host
 
     # roofline of the dominant kernel (tcgen05 all-pairs + filter): algorithmic FLOPs = 2*D per pair.  The kernel
