@@ -852,6 +852,7 @@ struct AggLayout {
   float* chatT; float* R; float* part; float* ssq; float* nrm; int* labels; int* cl_ptr; int* cl_tok; uint32_t* sup; uint16_t* memT; int* gcnt;
   int* cpred; double* norms; int* seg_off; long long* adj_off; int* grp_img; int* grp_seg0; int* grp_nseg;
   __nv_bfloat16* RT; int* tile_tbl;   // tensor-core path (aggregate_tc.cu)
+  double* xnorm;
   __nv_bfloat16* chat_planes;         // tensor-core assignment (assign_tc.cu)
   size_t total;
 };
@@ -881,6 +882,7 @@ static AggLayout carve_agg(void* ws, int B, int N, int D, int K, int S_total) {
   L.grp_nseg = c.take<int>(max_groups);
   L.RT = c.take<__nv_bfloat16>(agg_tc_supported(N, D, K) ? agg_tc_rt_elems(B, N, D) : 0);
   L.tile_tbl = c.take<int>((size_t)4 * agg_tc_max_tiles(B, S_total));
+  L.xnorm = c.take<double>(agg_tc_supported(N, D, K) ? agg_tc_xnorm_elems(B, S_total, D, K) : 0);
   L.chat_planes = c.take<__nv_bfloat16>(assign_tc_workspace_elems(D, K));
   L.total = c.total();
   return L;
@@ -1006,7 +1008,7 @@ static int aggregate_driver(const float* tokens, const float* residuals_in, cons
     ta.R = fused_rt ? nullptr : R; ta.tokens_dn = tokens; ta.centers = centers; ta.labels = L.labels; ta.nrm = L.nrm;
     ta.cl_ptr = L.cl_ptr; ta.cl_tok = L.cl_tok; ta.memS = L.memT; ta.cpred = L.cpred; ta.norms = L.norms;
     ta.seg_offsets_host = seg_offsets_host; ta.B = B; ta.N = N; ta.D = D; ta.K = K; ta.S_total = S_total;
-    ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl; ta.probe = g_agg_dbg;
+    ta.out = out; ta.out_dtype = out_dtype; ta.RT = L.RT; ta.tile_tbl = L.tile_tbl; ta.xnorm = L.xnorm; ta.probe = g_agg_dbg;
     ta.pca_mean = pca_mean;
     const int rc = agg_tc_run(ta, st);
     if (rc != SEGVLAD_OK) return rc;

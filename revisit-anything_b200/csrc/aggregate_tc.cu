@@ -28,13 +28,18 @@
 
 #include <stdlib.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "tc_ptx.cuh"
 
 namespace segvlad {
 
-constexpr int kTcThreadsAgg = 384;   // warps: 0 TMA, 1 MMA, 2-5 epilogue (column half 0), 6-7 mask builders, 8-11 epilogue (half 1)
+constexpr int kTcThreadsAgg = 384;   // warps: 0 TMA, 1 MMA, 2-3 mask builders | 4-7 epilogue (column half 0), 8-11 epilogue (half 1)
+// Register budget per warpgroup (setmaxnreg): the epilogue warps must not spill -- the kernel's shared memory leaves the L1 a
+// few KB, a spilled value comes back from L2, and under the kernel's own store traffic that round trip costs thousands of
+// cycles (r2: ~50 reloads per item in ~10 stall points cost more than the second sweep they were meant to save).
+constexpr int kTcRegsFront = 72, kTcRegsEpi = 216;   // per scheduler: 72 + 2 x 216 = 504 = 3 x 168, the CTA's own allocation (the pool)
 constexpr int kTcStages = 2;
 constexpr uint32_t kTcTileBytes = kTcSegTile * kTcTokChunk * 2;          // 16 KB: one [128 x 64] bf16 operand tile
 constexpr uint32_t kTcStageBytes = 4 * kTcTileBytes;                     // A + 3 B planes
@@ -43,8 +48,12 @@ constexpr double kEpsTc = 1e-12;
 
 constexpr uint32_t kTcBoxBytes = 32 * 128;                               // output staging box: 32 rows x 128 bytes
 constexpr uint32_t kTcStageOutBytes = 8 * 2 * kTcBoxBytes;               // 8 epilogue warps x 2 boxes
+constexpr int kTcTblTiles = 256;                                         // item tables cached in shared memory when they fit:
+constexpr int kTcTblCl = 2048;                                           // [tiles][4] and [B][K + 1] ints (12 KB)
+constexpr int kTcEarly = 6;                                              // sibling exchange prefetched into shared memory for J <= 6
 __host__ __device__ constexpr size_t agg_tc_smem() {
-  return 1024 + (size_t)kTcStages * kTcStageBytes + kTcStageOutBytes + 256 + 2 * 2 * kTcSegTile * 8;
+  return 1024 + (size_t)kTcStages * kTcStageBytes + kTcStageOutBytes + 256 + 2 * 2 * kTcSegTile * 8 +
+         4 * (4 * kTcTblTiles + kTcTblCl) + 2 * kTcEarly * kTcSegTile * 8 + 2 * 256 * 4;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,16 +156,17 @@ __device__ __forceinline__ void tc_fence_async_smem() { asm volatile("fence.prox
 // mbarrier wait that adds the cycles spent to a counter when the development probe is on
 // per-pass timeline of CTA 0 (development probe): probe[4096 + 8 * pass + j], j = 0 MMA: buffer free, 1 MMA: first operand
 // stage full, 2 MMA: pass committed, 3 producer: first stage of the pass issued, 4 epilogue (warp 2): accumulator full,
-// 5 epilogue: buffer handed back
+// 5 epilogue: buffer handed back; single-sweep items: 4 / 5 = front half (sum of squares), 6 / 7 = write pass begin / end
 #define TC_MARK(ti_, j_) do { if (kProbe && probe && blockIdx.x == 0 && (ti_) < 256) probe[4096 + 8 * (ti_) + (j_)] = clock64(); } while (0)
 #define TC_TIMED_WAIT(bar, par, acc) do { if (kProbe && probe) { const long long _t = clock64(); mbar_wait(bar, par); acc += clock64() - _t; } else mbar_wait(bar, par); } while (0)
 
 struct TcItem {
   int b, g0, s0, ns, k, p0, p1, rows, x0, nch, pj0, pj1;   // x0: p0 rounded down to 8 tokens (TMA needs 16-byte
-};                                                          // aligned global addresses); tokens < p0 are masked out
+  int res;                                                  // aligned global addresses); tokens < p0 are masked out
+};                                                          // res: single-sweep item (accumulators stay in TMEM), below
 // item id -> (segment tile, cluster, channel split); identical in every warp role
 __device__ __forceinline__ TcItem tc_item(int id, const int* __restrict__ tile_tbl, const int* __restrict__ cl_ptr, int K,
-                                          int J, int P) {
+                                          int J, int P, int resident) {
   TcItem it;
   const int j = id % J, rest = id / J;
   it.k = rest % K;
@@ -170,6 +180,11 @@ __device__ __forceinline__ TcItem tc_item(int id, const int* __restrict__ tile_t
   it.nch = (it.p1 - it.x0 + kTcTokChunk - 1) / kTcTokChunk;
   it.pj0 = (int)((long long)j * P / J);
   it.pj1 = (int)((long long)(j + 1) * P / J);
+  // Single-sweep ("resident") item: this CTA's channel passes (<= kTcBufs of them) each own a TMEM buffer, the contraction is
+  // issued ONCE, the epilogue takes the sums of squares from TMEM, exchanges them with the J - 1 sibling CTAs that hold the
+  // other channels of the same block, and then scales and writes the very same accumulators.  Needs one accumulator chain
+  // per pass (n_k <= kTcSubChunks chunks); longer clusters take the two-sweep path.  Identical in every role and sibling.
+  it.res = resident && it.nch <= kTcSubChunks && (P + J - 1) / J <= kTcBufs;
   return it;
 }
 
@@ -329,17 +344,30 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 template <typename OutT, bool kProbe, bool kPlanes>
 __global__ void __launch_bounds__(kTcThreadsAgg, 1)
 aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_constant__ CUtensorMap map_out,
-                    const int* __restrict__ tile_tbl,
-                    const int* __restrict__ cl_ptr, const uint16_t* __restrict__ memS, const int* __restrict__ cpred,
+                    const int* __restrict__ tile_tbl_g,
+                    const int* __restrict__ cl_ptr_g, const uint16_t* __restrict__ memS, const int* __restrict__ cpred,
                     int B, int N, int D, int K, int n_items, int J, OutT* __restrict__ out, double* __restrict__ norms,
                     unsigned long long* __restrict__ probe, int store_hint, const float* __restrict__ pca_mean,
-                    int S_total) {
+                    int S_total, int resident, double* xnorm) {
   extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_out = smem + kTcStages * kTcStageBytes;   // [8 epilogue warps][2 boxes][4 KB], 1024-byte aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kTcStageOutBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   double* s_ssq = reinterpret_cast<double*>(bars + 32);   // [2 item parities][2 column halves][128 rows] partial sums of squares
+  // Item tables in shared memory: every role looks an item up by two dependent loads, and under the kernel's own store
+  // traffic a round trip to L2 costs thousands of cycles -- per item, in every role's serial path (r2: ~10 k cycles per item)
+  int* s_tbl = reinterpret_cast<int*>(s_ssq + 2 * 2 * kTcSegTile);
+  double* s_x = reinterpret_cast<double*>(s_tbl + 4 * kTcTblTiles + kTcTblCl);   // [2 parities][kTcEarly siblings][128 rows]
+  int* s_cp = reinterpret_cast<int*>(s_x + 2 * kTcEarly * kTcSegTile);            // [2 parities][256 epilogue threads]
+  const int n_tiles = n_items / (K * J);
+  const bool tbl_fits = n_tiles <= kTcTblTiles && B * (K + 1) <= kTcTblCl;
+  if (tbl_fits) {
+    for (int i = threadIdx.x; i < 4 * n_tiles; i += blockDim.x) s_tbl[i] = tile_tbl_g[i];
+    for (int i = threadIdx.x; i < B * (K + 1); i += blockDim.x) s_tbl[4 * kTcTblTiles + i] = cl_ptr_g[i];
+  }
+  const int* tile_tbl = tbl_fits ? s_tbl : tile_tbl_g;
+  const int* cl_ptr = tbl_fits ? s_tbl + 4 * kTcTblTiles : cl_ptr_g;
   const uint32_t bar_full = smem_u32(bars + 0);      // [kTcStages] A written (2 builder warps) + B landed (TMA)
   const uint32_t bar_empty = smem_u32(bars + 4);     // [kTcStages] MMAs that read the stage retired
   const uint32_t bar_tfull = smem_u32(bars + 8);     // [kTcBufs]   accumulator pass complete
@@ -360,6 +388,8 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kTcRegsFront));
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -367,11 +397,11 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
       uint32_t stage = 0, phase = 0, tp = 0;
       long long t_wait = 0;
       for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
-        const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+        const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P, resident);
         if (it.rows == 0) continue;
-        const int n_inst = P + (it.pj1 - it.pj0);
+        const int n_inst = (it.res ? 0 : P) + (it.pj1 - it.pj0);
         for (int inst = 0; inst < n_inst; ++inst, ++tp) {
-          const int pass = inst < P ? inst : it.pj0 + inst - P;
+          const int pass = it.res ? it.pj0 + inst : (inst < P ? inst : it.pj0 + inst - P);
           // (r1: an L2 prefetch of the operand rows 1-3 passes ahead -- the norm sweep is their first touch, ~2.9 k cycles
           // per box from DRAM -- shortens the MMA's operand waits but costs more TMA time than it saves: 0.418 -> 0.434 /
           // 0.442 / 0.447 ms for a look-ahead of 1 / 2 / 3 passes; profiles/r1_agg_experiments.txt)
@@ -397,11 +427,11 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
       long long t_tempty = 0, t_full = 0;
       const long long t_begin = clock64();
       for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
-        const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+        const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P, resident);
         if (it.rows == 0) continue;
-        const int n_inst = P + (it.pj1 - it.pj0);
+        const int n_inst = (it.res ? 0 : P) + (it.pj1 - it.pj0);
         for (int inst = 0; inst < n_inst; ++inst) {
-          const int pass = inst < P ? inst : it.pj0 + inst - P;
+          const int pass = it.res ? it.pj0 + inst : (inst < P ? inst : it.pj0 + inst - P);
           const int width = min(kTcPassN, D - pass * kTcPassN);
           // kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major, N>>3 @17, M>>4 @24
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(width >> 3) << 17) |
@@ -447,17 +477,17 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
       if (kProbe && probe) { probe[blockIdx.x * 16 + 6] = t_tempty; probe[blockIdx.x * 16 + 7] = t_full;
                    probe[blockIdx.x * 16 + 8] = clock64() - t_begin; }
     }
-  } else if (warp == 6 || warp == 7) {
+  } else {
     // ===================== mask-tile builders (64 threads) =====================
-    const int u = threadIdx.x - 192;
+    const int u = threadIdx.x - 64;
     uint32_t stage = 0, phase = 0;
     long long t_bwait = 0;
     const long long t_bbegin = clock64();
     for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
-      const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+      const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P, resident);
       if (it.rows == 0) continue;
       const int ngrp = (it.ns + 7) >> 3;
-      const int n_inst = P + (it.pj1 - it.pj0);
+      const int n_inst = (it.res ? 0 : P) + (it.pj1 - it.pj0);
       uint32_t wlo[2][4];   // cached membership words of this thread's two (group, 8-token) cells: 8 x u16 each
       int cached_c = -1;
       for (int inst = 0; inst < n_inst; ++inst) {
@@ -504,8 +534,10 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         }
       }
     }
-    if (kProbe && probe && threadIdx.x == 192) { probe[blockIdx.x * 16 + 10] = t_bwait; probe[blockIdx.x * 16 + 11] = clock64() - t_bbegin; }
+    if (kProbe && probe && threadIdx.x == 64) { probe[blockIdx.x * 16 + 10] = t_bwait; probe[blockIdx.x * 16 + 11] = clock64() - t_bbegin; }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTcRegsEpi));
     // ===================== epilogue warps: thread = segment row (TMEM lane) =====================
     // Two warps per TMEM lane quarter, each owning 64 of a pass's 128 channels: one warp per scheduler could not hide
     // its own tcgen05.ld -> convert -> store latencies (r1 ncu: 12.5 % warps active, issue slots 19 % busy at 62 % of the
@@ -518,88 +550,193 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
     if (store_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_out));
     const bool tma_dims = (D % 64) == 0;      // every pass piece of this warp is 0 or 32 columns wide
     uint32_t ti = 0, n_done = 0, nbox = 0;
-    long long t_nwait = 0, t_bar = 0, t_wwait = 0, t_store = 0;
+    long long t_nwait = 0, t_bar = 0, t_wwait = 0, t_store = 0, t_xwait = 0;
     const long long t_ebegin = clock64();
-    for (int id = blockIdx.x; id < n_items; id += gridDim.x) {
-      const TcItem it = tc_item(id, tile_tbl, cl_ptr, K, J, P);
+    // Look-ahead over the sibling exchange (single-sweep items whose passes fill at most half of the TMEM): the partial sums
+    // of item i + 1 are posted BEFORE item i is written, so the wait for the siblings -- and the next item's MMAs -- hide
+    // behind a whole write sweep.  A CTA holds at most one posted-but-unwritten ("pending") item.
+    const bool la = resident && J > 1 && 2 * ((P + J - 1) / J) <= kTcBufs;
+    int pend_id = -1, pend_par = 0;
+    uint32_t pend_ti0 = 0;
+    TcItem pend_it = {};
+    const int e = half * kTcSegTile + row;                           // epilogue thread index
+    for (int id = blockIdx.x; id < n_items || pend_id >= 0;) {
+      const bool have = id < n_items;
+      TcItem cur = {};
+      if (have) cur = tc_item(id, tile_tbl, cl_ptr, K, J, P, resident);
+      // a two-sweep item cycles through every TMEM buffer: the pending item is written first (front = false: flush only)
+      const bool front = have && !(cur.rows != 0 && pend_id >= 0 && !(cur.res && la));
+      double ssq = 0.0;
+      const uint32_t cur_ti0 = ti;                                   // single-sweep item: first of its TMEM buffers
+      // The pending item's exchange slots (posted a write sweep ago) and this item's cluster counts are fetched into shared
+      // memory by cp.async while the front half runs: no L2 round trip (~1.5 k cycles under the kernel's own store traffic)
+      // sits in the epilogue's serial path, and none of it is held in registers (r2: register prefetch spilled, each load
+      // was waited for at once: 6 round trips per item).
+      const bool bfront = front && cur.rows != 0;                    // a front half with its barrier
+      const int par = n_done & 1;
+      bool early = false;
+      if (bfront) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(s_cp + par * 256 + e)),
+                     "l"(cpred + cur.s0 + (row < cur.ns ? row : 0)) : "memory");
+        if (pend_id >= 0 && J <= kTcEarly) {
+          early = true;
+          const double* xp = xnorm + (size_t)(pend_id - pend_id % J) * kTcSegTile;
+          for (int i = e; i < J * (kTcSegTile / 2); i += 256)       // 16-byte pieces, L2 only (the slots change during the kernel)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_x + par * kTcEarly * kTcSegTile + 2 * i)),
+                         "l"(xp + 2 * i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      if (front) {
+        if (cur.rows == 0) {
+          const bool valid = row < cur.ns;
+          const int s = cur.s0 + row;
+          OutT* orow = out + ((size_t)(valid ? s : cur.s0) * K + cur.k) * D;
+          // empty cluster: the block is zero for every segment
+          if (valid) {
+            if (cur.pj0 == 0 && half == 0) norms[(size_t)s * K + cur.k] = 0.0;
+            const int d_beg = cur.pj0 * kTcPassN, d_end = min(D, cur.pj1 * kTcPassN);
+            if constexpr (kPlanes) {
+              // zero block: the planes hold -mean
+              const size_t KD = (size_t)K * D;
+              for (int d = d_beg + 8 * half; d < d_end; d += 16) {
+                uint32_t xv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xv[j] = __float_as_uint(0.f - __ldg(pca_mean + (size_t)cur.k * D + d + j));
+                uint32_t o2[4], o1[4], o0[4];
+                tc_plane_chunk3(xv, 0, o0, o1, o2);
+                OutT* p0 = out + (size_t)s * KD + (size_t)cur.k * D + d;
+                *reinterpret_cast<uint4*>(p0) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                *reinterpret_cast<uint4*>(p0 + (size_t)S_total * KD) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<uint4*>(p0 + 2 * (size_t)S_total * KD) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+              }
+            } else {
+              for (int d = d_beg + 16 * half; d < d_end; d += 32) TcOut<OutT>::zero16(orow + d);
+            }
+          }
+          id += gridDim.x;
+          continue;
+        }
+        // ---- norm sweep: sum of squares of this warp's half of the block row (fp32 products, fp64 accumulation) ----
+        const int nsub = (cur.nch + kTcSubChunks - 1) / kTcSubChunks;   // accumulator chains per pass (1 unless n_k > ~128)
+        for (int pass = cur.res ? cur.pj0 : 0; pass < (cur.res ? cur.pj1 : P); ++pass) {
+          const int width = min(kTcPassN, D - pass * kTcPassN);
+          const int c0 = half * 64;
+          const int w0 = min(32, width - c0), w1 = min(32, width - c0 - 32);     // columns in this warp's two pieces
+          uint32_t va[32], vb[32];
+          for (int sub = 0; sub < nsub; ++sub, ++ti) {
+            const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
+            TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_nwait);
+            tc_fence_after();
+            if (warp == 4 && lane == 0) TC_MARK(ti, 4);
+            const uint32_t tcol = tlane + buf * kTcPassN + c0;
+            if (w0 > 0) {                                  // (warp-uniform)
+              if (sub == 0) {
+                tc_ld32_issue(tcol, va);
+                if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
+                tc_ld_wait(va);
+                if (w1 > 0) tc_ld_wait(vb);
+              } else {
+                tc_acc32(tcol, va);
+                if (w1 > 0) tc_acc32(tcol + 32, vb);
+              }
+            }
+            if (!cur.res) {                                  // (resident: the buffer keeps the accumulator for the write sweep)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            }
+            if (warp == 4 && lane == 0) TC_MARK(ti, 5);
+          }
+          if (w0 > 0) {
+            ssq += (double)tc_sumsq(va, w0);
+            if (w1 > 0) ssq += (double)tc_sumsq(vb, w1);
+          }
+        }
+        double* xs = s_ssq + (n_done & 1) * 2 * kTcSegTile;
+        xs[half * kTcSegTile + row] = ssq;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's prefetches: visible to all after the barrier
+        { const long long _t = (kProbe && probe) ? clock64() : 0;
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
+          if (kProbe && probe) t_bar += clock64() - _t; }
+        ssq = xs[row] + xs[kTcSegTile + row];
+        ++n_done;
+        if (cur.res && J > 1) {
+          // post this CTA's partial sums for the J - 1 sibling CTAs that hold the block's other channels: the 8-byte value is
+          // its own flag (the slots are preset to all-ones, which no sum of squares can be), so no fence and no counter --
+          // under the kernel's store traffic a fence costs thousands of cycles
+          if (half == 0)
+            asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(xnorm + (size_t)id * kTcSegTile + row),
+                         "l"(__double_as_longlong(ssq)) : "memory");
+        }
+      }
+      // ---- back half: scale and write (w = 0: the pending item, w = 1: the item whose front half just ran) ----
+      for (int w = 0; w < 2; ++w) {
+      int wid;
+      uint32_t ti0;
+      if (w == 0) {
+        if (pend_id < 0) continue;
+        wid = pend_id; ti0 = pend_ti0; pend_id = -1;
+      } else {
+        if (!front) continue;
+        if (cur.res && la) { pend_id = id; pend_ti0 = cur_ti0; pend_it = cur; pend_par = par; continue; }
+        wid = id; ti0 = cur_ti0;
+      }
+      const TcItem it = w == 0 ? pend_it : cur;
+      const int cp = s_cp[(w == 0 ? pend_par : par) * 256 + e];
       const bool valid = row < it.ns;
       const bool tma_rows = tma_dims && (quarter * 32 + 32 <= it.ns);
       const int s = it.s0 + row;
       OutT* orow = out + ((size_t)(valid ? s : it.s0) * K + it.k) * D;
-      if (it.rows == 0) {
-        // empty cluster: the block is zero for every segment
-        if (valid) {
-          if (it.pj0 == 0 && half == 0) norms[(size_t)s * K + it.k] = 0.0;
-          const int d_beg = it.pj0 * kTcPassN, d_end = min(D, it.pj1 * kTcPassN);
-          if constexpr (kPlanes) {
-            // zero block: the planes hold -mean
-            const size_t KD = (size_t)K * D;
-            for (int d = d_beg + 8 * half; d < d_end; d += 16) {
-              uint32_t xv[8];
+      const int nsub = (it.nch + kTcSubChunks - 1) / kTcSubChunks;
+      double tot = ssq;
+      if (it.res && J > 1) {
+        // the siblings' partial sums, added in sibling order: every sibling -- and every run -- gets the same bits.  Siblings
+        // are the CTAs of the J consecutive item ids; an item's wait depends only on posts of items with smaller ids + J, so
+        // the persistent grid (all CTAs resident: one per SM) cannot deadlock.
+        const long long t_x0 = (kProbe && probe) ? clock64() : 0;
+        const double* xp = xnorm + (size_t)(wid - wid % J) * kTcSegTile + row;
+        unsigned int polls = 0;
+        bool got = false;
+        tot = 0.0;
+        if (w == 0 && early) {
+          got = true;
+          const double* sx = s_x + par * kTcEarly * kTcSegTile + row;
+          for (int q = 0; q < J; ++q) {
+            const double v = sx[q * kTcSegTile];
+            got = got && __double_as_longlong(v) != -1ll;
+            tot += v;
+          }
+        }
+        if (!got) {                                       // immediate exchange, or a sibling more than a write sweep behind
+          tot = 0.0;
+          for (int j0 = 0; j0 < J; j0 += 4) {
+            unsigned long long v[4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) xv[j] = __float_as_uint(0.f - __ldg(pca_mean + (size_t)it.k * D + d + j));
-              uint32_t o2[4], o1[4], o0[4];
-              tc_plane_chunk3(xv, 0, o0, o1, o2);
-              OutT* p0 = out + (size_t)s * KD + (size_t)it.k * D + d;
-              *reinterpret_cast<uint4*>(p0) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-              *reinterpret_cast<uint4*>(p0 + (size_t)S_total * KD) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-              *reinterpret_cast<uint4*>(p0 + 2 * (size_t)S_total * KD) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            for (int q = 0; q < 4; ++q) {
+              v[q] = 0ull;
+              if (j0 + q < J) asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v[q]) : "l"(xp + (size_t)(j0 + q) * kTcSegTile) : "memory");
             }
-          } else {
-            for (int d = d_beg + 16 * half; d < d_end; d += 32) TcOut<OutT>::zero16(orow + d);
-          }
-        }
-        continue;
-      }
-      // ---- norm sweep: sum of squares of this warp's half of the block row (fp32 products, fp64 accumulation) ----
-      double ssq = 0.0;
-      const int nsub = (it.nch + kTcSubChunks - 1) / kTcSubChunks;   // accumulator chains per pass (1 unless n_k > ~128)
-      for (int pass = 0; pass < P; ++pass) {
-        const int width = min(kTcPassN, D - pass * kTcPassN);
-        const int c0 = half * 64;
-        const int w0 = min(32, width - c0), w1 = min(32, width - c0 - 32);     // columns in this warp's two pieces
-        uint32_t va[32], vb[32];
-        for (int sub = 0; sub < nsub; ++sub, ++ti) {
-          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-          TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_nwait);
-          tc_fence_after();
-          if (warp == 2 && lane == 0) TC_MARK(ti, 4);
-          const uint32_t tcol = tlane + buf * kTcPassN + c0;
-          if (w0 > 0) {                                  // (warp-uniform)
-            if (sub == 0) {
-              tc_ld32_issue(tcol, va);
-              if (w1 > 0) tc_ld32_issue(tcol + 32, vb);
-              tc_ld_wait(va);
-              if (w1 > 0) tc_ld_wait(vb);
-            } else {
-              tc_acc32(tcol, va);
-              if (w1 > 0) tc_acc32(tcol + 32, vb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              while (v[q] == ~0ull) {
+                asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v[q]) : "l"(xp + (size_t)(j0 + q) * kTcSegTile) : "memory");
+                if (++polls == (1u << 22)) __trap();      // a sibling never arrived: fail loudly instead of hanging the GPU
+              }
+              tot += __longlong_as_double((long long)v[q]);
             }
           }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-          if (warp == 2 && lane == 0) TC_MARK(ti, 5);
         }
-        if (w0 > 0) {
-          ssq += (double)tc_sumsq(va, w0);
-          if (w1 > 0) ssq += (double)tc_sumsq(vb, w1);
-        }
+        if (kProbe && probe) t_xwait += clock64() - t_x0;
       }
-      double* xs = s_ssq + (n_done & 1) * 2 * kTcSegTile;
-      xs[half * kTcSegTile + row] = ssq;
-      { const long long _t = (kProbe && probe) ? clock64() : 0;
-        asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 epilogue warps
-        if (kProbe && probe) t_bar += clock64() - _t; }
-      ssq = xs[row] + xs[kTcSegTile + row];
-      ++n_done;
-      const double nrm = sqrt(ssq);
+      const double nrm = sqrt(tot);
       double sc = 0.0;
       if (valid) {
         if (it.pj0 == 0 && half == 0) norms[(size_t)s * K + it.k] = nrm;
-        sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cpred[s]), kEpsTc));
+        sc = (1.0 / fmax(nrm, kEpsTc)) * (1.0 / fmax(sqrt((double)cp), kEpsTc));
       }
       // ---- write sweep: accumulator x scale -> fp64 -> 32-byte vector stores (each lane fills whole sectors of its row) ----
+      uint32_t tw = it.res ? ti0 : ti;                  // accumulator counter of the write sweep
       for (int pass = it.pj0; pass < it.pj1; ++pass) {
         const int width = min(kTcPassN, D - pass * kTcPassN);
         const int c0 = half * 64;
@@ -607,11 +744,13 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
         OutT* op = orow + (size_t)pass * kTcPassN + c0;
         uint32_t va[32], vb[32];
         long long t_s0 = 0;
-        for (int sub = 0; sub < nsub; ++sub, ++ti) {
-          const uint32_t buf = ti % kTcBufs, use = ti / kTcBufs;
-          TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_wwait);
-          tc_fence_after();
-          if (warp == 2 && lane == 0) TC_MARK(ti, 4);
+        for (int sub = 0; sub < nsub; ++sub, ++tw) {
+          const uint32_t buf = tw % kTcBufs, use = tw / kTcBufs;
+          if (!it.res) {                                  // (resident: complete since the norm phase)
+            TC_TIMED_WAIT(bar_tfull + 8 * buf, use & 1, t_wwait);
+            tc_fence_after();
+          }
+          if (warp == 4 && lane == 0) TC_MARK(tw, it.res ? 6 : 4);
           if (kProbe && sub == 0 && probe) t_s0 = clock64();
           const uint32_t tcol = tlane + buf * kTcPassN + c0;
           if (w0 > 0) {
@@ -734,13 +873,16 @@ aggregate_tc_kernel(const __grid_constant__ CUtensorMap map_rt, const __grid_con
           }
         }
         if (kProbe && probe) t_store += clock64() - t_s0;
-        if (warp == 2 && lane == 0) TC_MARK(ti - 1, 5);
+        if (warp == 4 && lane == 0) TC_MARK(tw - 1, it.res ? 7 : 5);
       }
+      if (!it.res) ti = tw;
+      }   // w
+      if (front) id += gridDim.x;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // staging boxes drained before exit
-    if (kProbe && probe && warp == 2 && lane == 0) {
+    if (kProbe && probe && warp == 4 && lane == 0) {
       unsigned long long* pr = probe + blockIdx.x * 16;
-      pr[0] = clock64() - t_ebegin; pr[1] = t_nwait; pr[3] = t_bar; pr[4] = t_wwait; pr[5] = t_store; pr[12] = n_done;
+      pr[0] = clock64() - t_ebegin; pr[1] = t_nwait; pr[3] = t_bar; pr[4] = t_wwait; pr[5] = t_store; pr[12] = n_done; pr[13] = t_xwait;
     }
   }
   tc_fence_before();
@@ -759,7 +901,8 @@ bool agg_tc_supported(int N, int D, int K) {
 }
 
 template <typename OutT, bool kPlanes>
-static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, int J, int grid, cudaStream_t st) {
+static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, int J, int grid, int resident,
+                     cudaStream_t st) {
   const size_t smem = agg_tc_smem();
   // L2 evict_first policy on the output stores: the output is a pure stream and should not push the operand planes, which
   // the write sweep re-reads, out of L2 (measured: 0.441 -> 0.427 ms on the bench workload).  "0" switches it off.
@@ -786,11 +929,40 @@ static int launch_tc(const AggTcArgs& a, const CUtensorMap& map, int n_items, in
   SV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int pslot = prof_begin(SEGVLAD_PROF_AGGREGATE, st);
   kern<<<grid, kTcThreadsAgg, smem, st>>>(map, map_out, a.tile_tbl, a.cl_ptr, a.memS, a.cpred, a.B, a.N, a.D, a.K, n_items, J,
-                                          reinterpret_cast<OutT*>(a.out), a.norms, a.probe, store_hint, a.pca_mean, a.S_total);
+                                          reinterpret_cast<OutT*>(a.out), a.norms, a.probe, store_hint, a.pca_mean, a.S_total,
+                                          resident, a.xnorm);
   prof_end(pslot, st);
   SV_CHECK_LAUNCH();
   return SEGVLAD_OK;
 }
+
+// Single-sweep launches wait for sibling CTAs inside the kernel, which is only safe while every CTA of the grid is resident.
+// Two such kernels running side by side on one GPU (two host threads, two streams) could each hold half of the SMs and wait
+// for CTAs that cannot start, so launches of one process on one device are chained on the GPU: a launch first waits for the
+// event of the previous one (no host blocking).  Other kernels may share the GPU: they finish and free their SMs.
+// (Kernels of OTHER processes running concurrently under MPS are not covered: set SEGVLAD_AGG_RESIDENT=0 there.)
+struct TcLaunchChain {
+  static constexpr int kMaxDev = 64;
+  static std::mutex& mu() { static std::mutex m; return m; }
+  static cudaEvent_t* events() { static cudaEvent_t ev[kMaxDev] = {}; return ev; }
+  bool on;
+  cudaStream_t st;
+  cudaEvent_t* ev = nullptr;
+  TcLaunchChain(bool enable, cudaStream_t s) : on(enable), st(s) {
+    if (!on) return;
+    mu().lock();
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { on = false; mu().unlock(); return; }
+    ev = events() + dev;
+    if (*ev) cudaStreamWaitEvent(st, *ev, 0);
+    else if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) *ev = nullptr;
+  }
+  ~TcLaunchChain() {
+    if (!on) return;
+    if (ev && *ev) cudaEventRecord(*ev, st);
+    mu().unlock();
+  }
+};
 
 int agg_tc_run(const AggTcArgs& a, cudaStream_t st) {
   static int num_sms = 0;
@@ -842,17 +1014,33 @@ int agg_tc_run(const AggTcArgs& a, cudaStream_t st) {
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SEGVLAD_ECUDA; }
 
   const int P = (a.D + kTcPassN - 1) / kTcPassN;
-  int J = 1;
+  // Single-sweep mode (r2): the channel passes of a block are split over J = ceil(P / 4) sibling CTAs so that each one's
+  // accumulators fit its TMEM and the contraction is issued once (tc_item).  "0" selects the two-sweep schedule of r1.
+  // With at most kTcBufs / 2 passes per CTA two items fit the TMEM and the sibling exchange of the next item hides behind the
+  // write sweep of the current one (look-ahead, "SEGVLAD_AGG_LA=1").  Measured slower than the immediate exchange with
+  // kTcBufs passes per CTA (0.398 vs 0.379 ms on the bench workload: twice the items, and each costs a front half), so off
+  // by default.
+  const char* re = getenv("SEGVLAD_AGG_RESIDENT");
+  const char* le = getenv("SEGVLAD_AGG_LA");
+  const int per_cta = (le && le[0] == '1') ? kTcBufs / 2 : kTcBufs;
+  const int Jres = (P + per_cta - 1) / per_cta;
+  const int resident = !(re && re[0] == '0') && Jres <= 32 && 2 * Jres <= num_sms;
+  int J = resident ? Jres : 1;
   while ((long long)nt * a.K * J < 2ll * num_sms && J * 2 <= P) J *= 2;   // few items: split the write sweep over channels
   const long long n_items = (long long)nt * a.K * J;
   SV_REQUIRE(n_items < (1ll << 31), "aggregate: too many work items");
   const int grid = (int)(n_items < num_sms ? n_items : num_sms);
+  // siblings of an item (J consecutive ids) wait for each other: the grid is never larger than the number of SMs and the
+  // kernel's shared memory allows one CTA per SM, so every CTA is resident
+  // (their exchange slots are preset to the all-ones pattern = "not posted yet")
+  if (resident && J > 1) SV_CHECK_CUDA(cudaMemsetAsync(a.xnorm, 0xFF, sizeof(double) * (size_t)n_items * kTcSegTile, st));
+  TcLaunchChain chain(resident && J > 1, st);
   if (a.out_dtype == SEGVLAD_OUT_PCA_PLANES) {
     SV_REQUIRE(a.pca_mean != nullptr && a.D % 64 == 0, "aggregate: the PCA-planes output needs the model mean and D_t %% 64 == 0");
-    return launch_tc<__nv_bfloat16, true>(a, map, (int)n_items, J, grid, st);
+    return launch_tc<__nv_bfloat16, true>(a, map, (int)n_items, J, grid, resident, st);
   }
-  return a.out_dtype == SEGVLAD_OUT_F64 ? launch_tc<double, false>(a, map, (int)n_items, J, grid, st)
-                                        : launch_tc<float, false>(a, map, (int)n_items, J, grid, st);
+  return a.out_dtype == SEGVLAD_OUT_F64 ? launch_tc<double, false>(a, map, (int)n_items, J, grid, resident, st)
+                                        : launch_tc<float, false>(a, map, (int)n_items, J, grid, resident, st);
 }
 
 }  // namespace segvlad

@@ -34,12 +34,16 @@ struct AggTcArgs {
   const float* pca_mean;      // (descriptor - pca_mean) [fp32 copy of the model mean], the A operand of the tensor-core PCA projection (row f1)
   __nv_bfloat16* RT;          // workspace: [3 planes][B][D][Np] transposed, label-sorted bf16 split of R
   int* tile_tbl;              // workspace: [n_tiles][4] = image, first group, first segment, #segments
+  double* xnorm;              // workspace: [n_items][128] per-CTA partial sums of squares of the single-sweep items (sibling exchange)
   unsigned long long* probe;  // development aid: per-CTA cycle counters [grid][16] (segvlad_debug_aggregate_probe), or null
 };
 
 inline int agg_tc_np(int N) { return (int)align_up((size_t)N, kTcTokChunk); }
 inline size_t agg_tc_rt_elems(int B, int N, int D) { return (size_t)3 * B * D * agg_tc_np(N); }
 inline int agg_tc_max_tiles(int B, int S_total) { return S_total / kTcSegTile + B; }
+inline size_t agg_tc_xnorm_elems(int B, int S_total, int D, int K) {       // channel splits J <= number of passes
+  return (size_t)agg_tc_max_tiles(B, S_total) * K * ((D + kTcPassN - 1) / kTcPassN) * kTcSegTile;
+}
 bool agg_tc_supported(int N, int D, int K);
 int agg_tc_fused_channels(int N, int K);               // > 0: RT can be built straight from [D][N] tokens
 int agg_tc_run(const AggTcArgs& a, cudaStream_t st);   // returns SEGVLAD_* status

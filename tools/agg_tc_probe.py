@@ -25,6 +25,6 @@ a = a[a[:, 0] > 0]
 print("CTAs", len(a))
 names = {0: "epi total", 1: "epi wait tfull (norm sweep)", 3: "epi bar.sync", 4: "epi wait tfull (write sweep)",
          5: "epi ld+stage+store (write sweep)", 6: "mma wait tempty", 7: "mma wait full", 8: "mma total",
-         9: "producer wait empty", 10: "builder wait empty", 11: "builder total", 12: "items"}
+         9: "producer wait empty", 10: "builder wait empty", 11: "builder total", 12: "items", 13: "epi sibling exchange wait"}
 for i, n in names.items():
     print(f"{n:36s} mean {a[:, i].mean():12.0f}  min {a[:, i].min():10d}  max {a[:, i].max():10d}")

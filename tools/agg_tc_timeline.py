@@ -22,7 +22,7 @@ torch.cuda.synchronize()
 lib.segvlad_debug_aggregate_probe(None)
 t = buf.cpu().numpy()[4096:].reshape(256, 8)
 t0 = t[0, 3] if t[0, 3] else t[0, 0]
-names = ["mma:buf_free", "mma:stage_full", "mma:committed", "prod:issued", "epi:acc_full", "epi:released"]
+names = ["mma:buf_free", "mma:stage_full", "mma:committed", "prod:issued", "epi:acc_full", "epi:released", "epi:write_beg", "epi:write_end"]
 print("pass " + " ".join(f"{n:>15s}" for n in names) + "   (cycles since the first TMA issue; passes 0-11 norm sweep, 12-23 write sweep, ...)")
 for i in range(int(os.environ.get("NPASS", 60))):
-    print(f"{i:4d} " + " ".join(f"{int(t[i, j] - t0):15d}" for j in range(6)))
+    print(f"{i:4d} " + " ".join(f"{int(t[i, j] - t0) if t[i, j] else 0:15d}" for j in range(8)))
