@@ -12,6 +12,6 @@ for line in sys.stdin:
         print('$1', 'kernel_ms', a['kernel_ms'], 'frac', a['roofline']['frac'], 'batch_ms', a['ms_per_batch'], 'fused', f.get('fused'))"
 }
 run default
-SEGVLAD_AGG_LA=0 run la0
+SEGVLAD_AGG_LA=1 run lookahead
 SEGVLAD_AGG_RESIDENT=0 run res0
 tail -3 gpurun_out/res_default.err
