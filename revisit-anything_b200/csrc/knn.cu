@@ -46,9 +46,9 @@ constexpr int kMaxK = 1024;
 constexpr int kExactFlag = (int)0x80000000;  // cand_idx sign bit: this candidate's d2 is already the exact fp32 value
 constexpr int kQueryBlock = 16384; // query rows per pass (bounds the workspace)
 constexpr int kTileM = 128, kTileN = 256, kTileK = 64;
-constexpr int kTcThreads = 320;    // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-9 epilogue (2 per TMEM lane quarter)
-constexpr int kTcThreadsWide = 576; // ... or 16 epilogue warps (4 per lane quarter, 64 columns each): shallow contractions
-                                    // (D <= 1024), where a tile's MMAs are too short to hide an 8-warp epilogue
+// filter kernel threads = 32 * (2 + kEpi): warp0 TMA, warp1 MMA (+TMEM alloc), then kEpi = 8 epilogue warps (2 per TMEM lane
+// quarter) or 16 (4 per lane quarter, 64 columns each) for shallow contractions (D <= 1024), where a tile's MMAs are too
+// short to hide an 8-warp epilogue
 
 struct SelState {
   float* tau;      // [rows] current k-th best d2 (+inf until k candidates seen)
