@@ -80,6 +80,28 @@ def test_pack_roundtrip():
         D.pack_topk(d2, torch.tensor([[2 ** 31, 0, 0]], dtype=torch.int64))
 
 
+def test_pack_order_property():
+    # property behind the k-way merge of packed lists: integer order of the keys == (d2 ascending, then row as uint32
+    # ascending: the -1 padding last), and the round trip is exact -- for any non-negative fp32 d2 (zero, sub-normal, inf)
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+
+    @hyp.settings(max_examples=200, deadline=None)
+    @hyp.given(st.lists(st.tuples(st.floats(min_value=0.0, allow_nan=False, width=32), st.integers(-1, 2 ** 31 - 1)),
+                        min_size=1, max_size=48))
+    def check(pairs):
+        d2 = torch.tensor([[p[0] for p in pairs]], dtype=torch.float32)
+        idx = torch.tensor([[p[1] for p in pairs]], dtype=torch.int64)
+        keys = D.pack_topk(d2, idx)
+        a, b = D.unpack_topk(keys)
+        assert torch.equal(a.view(torch.int32), d2.view(torch.int32)) and torch.equal(b, idx)
+        want = sorted(range(len(pairs)), key=lambda i: (float(d2[0, i]), int(idx[0, i]) & 0xFFFFFFFF, i))
+        got = sorted(range(len(pairs)), key=lambda i: (int(keys[0, i]), i))
+        assert want == got
+
+    check()
+
+
 @pytest.mark.parametrize("world,k", [(2, 64), (4, 80)])
 def test_world2_gloo_matches_single_process(world, k):
     # world 4: uneven shards (75, 75, 75, 74 rows), each SHORTER than k = 80 -> padded (+inf, -1) lists enter the merge
