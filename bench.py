@@ -304,6 +304,8 @@ def aggregation_side_bench(device, peaks, cpu=True):
     out = {"workload": f"{B} images x {S} SuperSegments, N={N}, D_t={D}, K={K}, fp64 out, density 0.5",
            "superseg_per_s": B * S / (ms * 1e-3), "ms_per_batch": ms, "kernel_ms": kern_ms,
            "algorithmic_bytes_per_image": bytes_img,
+           "schedule": ("two_sweeps" if os.environ.get("SEGVLAD_AGG_RESIDENT", "1")[:1] == "0" else
+                        "single_sweep_lookahead" if os.environ.get("SEGVLAD_AGG_LA", "0")[:1] == "1" else "single_sweep"),
            "roofline": {"bound": "hbm", "kernel": "aggregate_tc_kernel", "achieved": B * bytes_img / (kern_ms * 1e-3) / 1e9,
                         "peak": hbm, "unit": "GB/s", "frac": B * bytes_img / (kern_ms * 1e-3) / 1e9 / hbm,
                         "batch_achieved": B * bytes_img / (ms * 1e-3) / 1e9,
