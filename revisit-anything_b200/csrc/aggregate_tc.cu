@@ -13,17 +13,23 @@
 //   * one CTA owns (image, tile of 128 segments, cluster): A = mask tile [128 x 64 tokens] written into shared memory
 //     by two builder warps from the membership words, B = [128 channels x 64 tokens] x 3 planes by TMA, D = fp32
 //     accumulators in TMEM (4 buffers of 128 columns);
-//   * the block norm needs all D channels but TMEM holds 512 of them, so the contraction is issued twice -- a norm
-//     sweep (TMEM -> sum of squares, no stores) and a write sweep (TMEM -> x scale -> fp64 -> 256-bit global stores;
-//     r1: 256-byte bulk stores through a staging buffer were bound by the TMA request rate, ~6 k requests per item).
-//     The tensor work is ~10 % of the write time, the operand re-read comes from L2;
-//   * thread = segment row (TMEM lane), so norms and scales never leave the thread: no reductions, no CTA barriers.
+//   * the block norm needs all D channels but TMEM holds 512 of them.  Single sweep (r2, default): the channel passes of
+//     a block are split over J = ceil(P / 4) sibling CTAs, each keeps its <= 4 accumulators in TMEM, the contraction is
+//     issued ONCE, the siblings exchange their partial sums of squares through a small global workspace (a posted value is
+//     its own flag) and then scale and write the same accumulators (TMEM -> x scale -> fp64 -> staging box -> bulk tensor
+//     store).  Clusters with more than 128 tokens, and SEGVLAD_AGG_RESIDENT=0, take the two-sweep schedule of r1: a norm
+//     sweep (TMEM -> sum of squares, no stores) and a write sweep with the contraction issued twice (the operand re-read
+//     comes from L2).  The tensor work is ~10 % of the write time either way;
+//   * thread = segment row (TMEM lane), so norms and scales never leave the thread (the two column halves of a row meet in
+//     shared memory once per item).
 // Accumulation is fp32 in TMEM (truncating adds, measured ~4e-8..6e-8 relative per MMA).  The length of one accumulator
 // chain is bounded (kTcSubChunks chunks = 128 tokens = 24 MMAs, <= 2.9e-6 relative): a cluster with more tokens -- a
 // sky / road dominated image, the whole-image AnyLoc VLAD -- is accumulated as several chains in successive TMEM buffers
 // whose partial sums the epilogue adds in registers (fp32 round-to-nearest), so the error does not grow with n_k and
-// stays inside the 1e-5 descriptor tolerance for any vocabulary; the planes are accumulated small-to-large.  Warp roles: 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-5 and 8-11 epilogue (two warps per TMEM
-// lane quarter, 64 channels of a pass each), 6-7 mask-tile builders.
+// stays inside the 1e-5 descriptor tolerance for any vocabulary; the planes are accumulated small-to-large.
+// Warp roles: warpgroup 0 = warp 0 TMA producer, 1 MMA issuer (+TMEM alloc), 2-3 mask-tile builders (72 registers);
+// warpgroups 1-2 = epilogue, warps 4-7 and 8-11 (two warps per TMEM lane quarter, 64 channels of a pass each; 216 registers:
+// a spill in the epilogue costs an L2 round trip under the kernel's own store traffic).
 #include "aggregate_tc.cuh"
 
 #include <stdlib.h>
